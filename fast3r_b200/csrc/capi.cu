@@ -1,0 +1,217 @@
+// extern "C" boundary of libfast3r_b200.so (see include/fast3r_b200.h).  Builds the TMA descriptors
+// (cuTensorMapEncodeTiled through cudaGetDriverEntryPoint, so libcuda is not a link-time dependency),
+// validates arguments and enqueues the kernels on the caller's stream.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/fast3r_b200.h"
+#include "f3r_kernels.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+
+int fail(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return 1;
+}
+int check(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return 0;
+  return fail("%s: %s", what, cudaGetErrorString(e));
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+// bf16 tensor map, 128B swizzle, zero OOB fill.  dims[0] is the contiguous dimension.
+int make_tmap(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+              const uint32_t* box) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail("cuTensorMapEncodeTiled not available (no CUDA driver?)");
+  cuuint64_t gd[5];
+  cuuint64_t gs[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i < rank - 1; ++i) gs[i] = strides_bytes[i];
+  if (reinterpret_cast<uintptr_t>(ptr) & 15) return fail("tensor map base not 16-byte aligned");
+  for (int i = 0; i < rank - 1; ++i)
+    if (gs[i] % 16) return fail("tensor map stride %d (%llu B) not a multiple of 16", i, (unsigned long long)gs[i]);
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), gd, gs, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
+  return 0;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n) return n;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  return n;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* f3r_last_error(void) { return g_err; }
+int f3r_abi_version(void) { return F3R_ABI_VERSION; }
+uint64_t f3r_launch_count(void) { return g_launches.load(); }
+
+int f3r_gemm(const f3r_gemm_desc* d, void* stream) {
+  if (!d || !d->a || !d->wt) return fail("f3r_gemm: null operand");
+  if (d->n <= 0 || d->k <= 0 || d->w <= 0 || d->h <= 0 || d->nb <= 0) return fail("f3r_gemm: bad shape");
+  if (d->n % 32) return fail("f3r_gemm: n=%d must be a multiple of 32", d->n);
+  if (d->k % 8 || d->a_ld % 8) return fail("f3r_gemm: k=%d and a_ld=%d must be multiples of 8", d->k, d->a_ld);
+  if (d->taps != 1 && d->taps != 9) return fail("f3r_gemm: taps must be 1 or 9");
+  if (d->epi == F3R_EPI_FINAL && d->n != 128) return fail("f3r_gemm: FINAL epilogue needs n == 128");
+  if (d->epi == F3R_EPI_CONVT && (d->ct_k <= 0 || d->ct_cout % 32 || d->n != d->ct_k * d->ct_k * d->ct_cout))
+    return fail("f3r_gemm: bad CONVT geometry");
+  if (d->epi == F3R_EPI_ROPE && (!d->rope_cos || !d->rope_sin || d->tok_per_img <= 0 || d->grid_w <= 0))
+    return fail("f3r_gemm: bad ROPE arguments");
+  if (d->epi == F3R_EPI_IDXEMB && (!d->emb_table || !d->emb_ids || d->tok_per_img <= 0))
+    return fail("f3r_gemm: bad IDXEMB arguments");
+
+  f3r::GemmArgs a;
+  memset(&a, 0, sizeof(a));
+  a.M = d->w * d->h * d->nb; a.N = d->n; a.K = d->k; a.taps = d->taps;
+  a.W = d->w; a.H = d->h; a.NB = d->nb;
+  // pixel tile (bw x bh = 128) minimising the number of tiles
+  int best_bw = 128; long best_tiles = -1;
+  for (int bw = 128; bw >= 1; bw >>= 1) {
+    const int bh = 128 / bw;
+    const long tiles = static_cast<long>((d->w + bw - 1) / bw) * ((d->h + bh - 1) / bh);
+    if (best_tiles < 0 || tiles < best_tiles) { best_tiles = tiles; best_bw = bw; }
+  }
+  a.bw = best_bw; a.bh = 128 / best_bw;
+  a.tiles_x = (d->w + a.bw - 1) / a.bw; a.tiles_y = (d->h + a.bh - 1) / a.bh;
+  a.num_m_tiles = a.tiles_x * a.tiles_y * d->nb;
+  int block_n = 128;
+  if (d->epi != F3R_EPI_FINAL && d->n > 128) {
+    const long tiles256 = static_cast<long>(a.num_m_tiles) * ((d->n + 255) / 256);
+    if (tiles256 >= num_sms()) block_n = 256;
+  }
+  a.num_n_tiles = (d->n + block_n - 1) / block_n;
+  a.epi = d->epi; a.act = d->act; a.out0_f32 = d->out0_f32; a.res0_f32 = d->res0_f32;
+  a.ldo = d->ldo > 0 ? d->ldo : d->n;
+  a.split_col = d->split_col; a.ldo_b = d->ldo_b;
+  a.tok_per_img = d->tok_per_img; a.grid_w = d->grid_w; a.rope_cols = d->rope_cols;
+  a.ct_k = d->ct_k; a.ct_cout = d->ct_cout;
+  a.bias = d->bias; a.res0 = d->res0; a.res1 = d->res1;
+  a.out0 = d->out0; a.out0b = d->out0b; a.out1 = d->out1;
+  a.rope_cos = d->rope_cos; a.rope_sin = d->rope_sin;
+  a.emb_table = d->emb_table; a.emb_ids = d->emb_ids;
+  a.w4 = d->w4; a.b4 = d->b4; a.pts = d->pts; a.conf = d->conf;
+  if (a.split_col && (a.split_col % 32 || !a.out0b)) return fail("f3r_gemm: bad column split");
+
+  CUtensorMap ta, tb;
+  {
+    const uint64_t ld = static_cast<uint64_t>(d->a_ld) * 2;
+    const uint64_t dims[4] = {static_cast<uint64_t>(d->k), static_cast<uint64_t>(d->w),
+                              static_cast<uint64_t>(d->h), static_cast<uint64_t>(d->nb)};
+    const uint64_t str[3] = {ld, ld * d->w, ld * d->w * d->h};
+    const uint32_t box[4] = {64, static_cast<uint32_t>(a.bw), static_cast<uint32_t>(a.bh), 1};
+    if (make_tmap(&ta, d->a, 4, dims, str, box)) return 1;
+  }
+  {
+    const uint64_t dims[3] = {static_cast<uint64_t>(d->k), static_cast<uint64_t>(d->taps),
+                              static_cast<uint64_t>(d->n)};
+    const uint64_t str[2] = {static_cast<uint64_t>(d->k) * 2, static_cast<uint64_t>(d->k) * 2 * d->taps};
+    const uint32_t box[3] = {64, 1, static_cast<uint32_t>(block_n)};
+    if (make_tmap(&tb, d->wt, 3, dims, str, box)) return 1;
+  }
+  g_launches++;
+  return check(f3r::launch_gemm(block_n, ta, tb, a, num_sms(), static_cast<cudaStream_t>(stream)), "f3r_gemm");
+}
+
+int f3r_attention(const void* q, int32_t ldq, const void* kv, int32_t ldkv, void* out, int32_t ldo, float* lse,
+                  int32_t batch, int32_t heads, int32_t sq, int32_t skv, float scale, void* stream) {
+  if (!q || !kv || !out) return fail("f3r_attention: null operand");
+  if (batch <= 0 || heads <= 0 || sq <= 0 || skv <= 0) return fail("f3r_attention: bad shape");
+  if (ldq % 8 || ldkv % 8 || ldo % 8 || ldq < heads * 64 || ldkv < 2 * heads * 64 || ldo < heads * 64)
+    return fail("f3r_attention: bad leading dimensions");
+  CUtensorMap tq, tkv;
+  {
+    const uint64_t dims[3] = {static_cast<uint64_t>(heads) * 64, static_cast<uint64_t>(sq),
+                              static_cast<uint64_t>(batch)};
+    const uint64_t str[2] = {static_cast<uint64_t>(ldq) * 2, static_cast<uint64_t>(ldq) * 2 * sq};
+    const uint32_t box[3] = {64, 128, 1};
+    if (make_tmap(&tq, q, 3, dims, str, box)) return 1;
+  }
+  {
+    const uint64_t dims[3] = {static_cast<uint64_t>(heads) * 128, static_cast<uint64_t>(skv),
+                              static_cast<uint64_t>(batch)};
+    const uint64_t str[2] = {static_cast<uint64_t>(ldkv) * 2, static_cast<uint64_t>(ldkv) * 2 * skv};
+    const uint32_t box[3] = {64, 128, 1};
+    if (make_tmap(&tkv, kv, 3, dims, str, box)) return 1;
+  }
+  f3r::AttnArgs a;
+  memset(&a, 0, sizeof(a));
+  a.batch = batch; a.heads = heads; a.sq = sq; a.skv = skv;
+  a.q_tiles = (sq + 255) / 256;
+  a.scale_log2 = scale * 1.4426950408889634f;
+  a.ldo = ldo; a.out = out; a.lse = lse;
+  g_launches++;
+  return check(f3r::launch_attention(tq, tkv, a, static_cast<cudaStream_t>(stream)), "f3r_attention");
+}
+
+int f3r_layernorm(const float* x, const float* w, const float* b, void* out, int32_t out_f32, int32_t rows,
+                  int32_t dim, float eps, void* stream) {
+  if (!x || !w || !b || !out) return fail("f3r_layernorm: null operand");
+  g_launches++;
+  return check(f3r::launch_layernorm(x, w, b, out, out_f32, rows, dim, eps, static_cast<cudaStream_t>(stream)),
+               "f3r_layernorm (dim must be one of 128,256,384,512,768,1024)");
+}
+
+int f3r_im2col_patch(const float* img, void* out, int32_t n, int32_t h, int32_t w, void* stream) {
+  if (!img || !out) return fail("f3r_im2col_patch: null operand");
+  g_launches++;
+  return check(f3r::launch_im2col_patch(img, out, n, h, w, 16, static_cast<cudaStream_t>(stream)),
+               "f3r_im2col_patch");
+}
+
+int f3r_im2col3x3s2(const void* in, void* out, int32_t n, int32_t h, int32_t w, int32_t c, int32_t ho, int32_t wo,
+                    void* stream) {
+  if (!in || !out) return fail("f3r_im2col3x3s2: null operand");
+  g_launches++;
+  return check(f3r::launch_im2col3x3s2(in, out, n, h, w, c, ho, wo, static_cast<cudaStream_t>(stream)),
+               "f3r_im2col3x3s2");
+}
+
+int f3r_upsample2x(const void* in, void* out, int32_t n, int32_t h, int32_t w, int32_t c, int32_t ho, int32_t wo,
+                   void* stream) {
+  if (!in || !out) return fail("f3r_upsample2x: null operand");
+  if (ho > 2 * h || wo > 2 * w) return fail("f3r_upsample2x: window larger than the x2 output");
+  g_launches++;
+  return check(f3r::launch_upsample2x(in, out, n, h, w, c, ho, wo, 2 * h, 2 * w, static_cast<cudaStream_t>(stream)),
+               "f3r_upsample2x");
+}
+
+int f3r_cast_bf16(const float* in, void* out, size_t count, void* stream) {
+  if (!in || !out) return fail("f3r_cast_bf16: null operand");
+  g_launches++;
+  return check(f3r::launch_cast_bf16(in, out, count, static_cast<cudaStream_t>(stream)), "f3r_cast_bf16");
+}
+
+}  // extern "C"

@@ -1,0 +1,59 @@
+// Internal launch interfaces between capi.cu and the kernel translation units.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace f3r {
+
+enum { EPI_STORE = 0, EPI_ROPE = 1, EPI_IDXEMB = 2, EPI_CONVT = 3, EPI_FINAL = 4 };
+enum { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2 };
+
+struct GemmArgs {
+  int M, N, K, taps;
+  int W, H, NB, bw, bh, tiles_x, tiles_y;
+  int num_m_tiles, num_n_tiles;
+  int epi, act, out0_f32, res0_f32;
+  int ldo;               // row stride (elements) of out0 / out1 / res0 / res1
+  int split_col, ldo_b;  // columns >= split_col go to out0b (row stride ldo_b); 0 = no split
+  int tok_per_img, grid_w, rope_cols;  // EPI_ROPE / EPI_IDXEMB
+  int ct_k, ct_cout;                   // EPI_CONVT
+  const float* bias;
+  const void* res0;
+  const void* res1;
+  void* out0;
+  void* out0b;
+  void* out1;
+  const float* rope_cos;
+  const float* rope_sin;
+  const float* emb_table;
+  const int* emb_ids;
+  const float* w4;
+  const float* b4;
+  float* pts;
+  float* conf;
+};
+
+cudaError_t launch_gemm(int block_n, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, int num_sms,
+                        cudaStream_t stream);
+
+struct AttnArgs {
+  int batch, heads, sq, skv;  // per-batch query / key lengths
+  int q_tiles;                // ceil(sq / 256)
+  float scale_log2;           // softmax scale * log2(e)
+  int ldo;                    // row stride of out (elements)
+  void* out;                  // bf16 [batch*sq, ldo], head h at columns h*64
+  float* lse;                 // optional fp32 [batch, heads, sq] log-sum-exp (natural log)
+};
+cudaError_t launch_attention(const CUtensorMap& tq, const CUtensorMap& tkv, const AttnArgs& a, cudaStream_t stream);
+
+cudaError_t launch_layernorm(const float* x, const float* w, const float* b, void* out, int out_f32, int rows,
+                             int dim, float eps, cudaStream_t stream);
+cudaError_t launch_im2col_patch(const float* img, void* out, int n, int H, int W, int patch, cudaStream_t stream);
+cudaError_t launch_im2col3x3s2(const void* in, void* out, int n, int H, int W, int C, int Ho, int Wo,
+                               cudaStream_t stream);
+cudaError_t launch_upsample2x(const void* in, void* out, int n, int H, int W, int C, int Ho, int Wo, int Hfull,
+                              int Wfull, cudaStream_t stream);
+cudaError_t launch_cast_bf16(const float* in, void* out, size_t n, cudaStream_t stream);
+
+}  // namespace f3r

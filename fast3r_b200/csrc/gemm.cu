@@ -1,0 +1,330 @@
+// Persistent warp-specialised tcgen05 GEMM / implicit-GEMM convolution for sm_100a.
+//
+//   out[m, n] = epilogue( sum_{tap, k} A[pixel(m) + shift(tap), k] * Wt[n, tap, k] )
+//
+// A is a channels-last bf16 activation viewed as (C, W, H, NB) and fetched by 4-D TMA boxes of
+// 128 pixels x 64 channels (out-of-bounds pixels/channels are zero-filled by TMA, which gives the
+// 3x3 zero padding and the K / N tails for free).  A plain linear layer is the 1-tap case with
+// W = rows.  Accumulation happens in TMEM (two BLOCK_N-column stages so the epilogue of tile i
+// overlaps the MMAs of tile i+1); one elected thread issues tcgen05.mma, one thread issues TMA.
+//
+// Covers (reference file:line in DESIGN.md): nn.Linear qkv/proj/fc1/fc2/decoder_embed
+// (fast3r/croco/models/blocks.py:94-97,125-128; fast3r/models/fast3r.py:673), patch-embed conv as
+// im2col GEMM (blocks.py:412), DPT 1x1 / 3x3 / transposed convs (fast3r/croco/models/dpt_block.py).
+#include "common.cuh"
+#include "f3r_kernels.h"
+
+namespace f3r {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;
+constexpr int GEMM_THREADS = 192;  // warp0 TMA, warp1 MMA(+TMEM alloc), warps 2-5 epilogue
+
+template <int BLOCK_N>
+struct GemmCfg {
+  static constexpr int kStages = (BLOCK_N == 256) ? 4 : 6;
+  static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
+  static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr uint32_t kTmemCols = 2 * BLOCK_N;
+};
+
+template <int BLOCK_N>
+__device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, float (&v)[32], int m, int col0, bool row_ok,
+                                               int img, int py, int px, float (&fin)[4]) {
+  // ---- bias
+  if (p.bias != nullptr) {
+    const float4* b4 = reinterpret_cast<const float4*>(p.bias + (p.epi == EPI_CONVT ? (col0 % p.ct_cout) : col0));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float4 b = __ldg(b4 + i);
+      v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+    }
+  }
+  if (!row_ok) return;
+
+  if (p.epi == EPI_ROPE && col0 < p.rope_cols) {
+    // RoPE2D (fast3r/croco/models/pos_embed.py:141-183): 32-wide half-head, pair (j, j+16), angle pos*base^(-j/16)
+    const int t = m % p.tok_per_img;
+    const int pos = ((col0 >> 5) & 1) ? (t % p.grid_w) : (t / p.grid_w);
+    const float4* c4 = reinterpret_cast<const float4*>(p.rope_cos + pos * 16);
+    const float4* s4 = reinterpret_cast<const float4*>(p.rope_sin + pos * 16);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float4 c = __ldg(c4 + i), s = __ldg(s4 + i);
+      float cc[4] = {c.x, c.y, c.z, c.w}, ss[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int j = 4 * i + e;
+        const float a = v[j], b = v[j + 16];
+        v[j] = a * cc[e] - b * ss[e];
+        v[j + 16] = b * cc[e] + a * ss[e];
+      }
+    }
+  }
+  if (p.epi == EPI_IDXEMB) {
+    // + image_idx_emb[id(view of token)]  (fast3r/models/fast3r.py:785-799)
+    const int id = __ldg(p.emb_ids + m / p.tok_per_img);
+    const float4* e4 = reinterpret_cast<const float4*>(p.emb_table + static_cast<size_t>(id) * p.N + col0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float4 e = __ldg(e4 + i);
+      v[4 * i + 0] += e.x; v[4 * i + 1] += e.y; v[4 * i + 2] += e.z; v[4 * i + 3] += e.w;
+    }
+  }
+  if (p.epi == EPI_FINAL) {
+    // ReLU -> conv1x1 (BLOCK_N -> 4), accumulated across the column chunks of this row
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float r = fmaxf(v[i], 0.f);
+#pragma unroll
+      for (int o = 0; o < 4; ++o) fin[o] = fmaf(r, __ldg(p.w4 + o * p.N + col0 + i), fin[o]);
+    }
+    return;
+  }
+
+  // ---- residual adds
+  size_t off;
+  if (p.epi == EPI_CONVT) {
+    const int ij = col0 / p.ct_cout, o0 = col0 % p.ct_cout, k = p.ct_k;
+    const int oy = py * k + ij / k, ox = px * k + ij % k;
+    off = ((static_cast<size_t>(img) * p.H * k + oy) * (p.W * k) + ox) * p.ct_cout + o0;
+  } else {
+    off = static_cast<size_t>(m) * p.ldo + col0;
+  }
+  if (p.res0 != nullptr) {
+    if (p.res0_f32) {
+      const float4* r4 = reinterpret_cast<const float4*>(static_cast<const float*>(p.res0) + off);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float4 r = r4[i];
+        v[4 * i + 0] += r.x; v[4 * i + 1] += r.y; v[4 * i + 2] += r.z; v[4 * i + 3] += r.w;
+      }
+    } else {
+      const uint4* r4 = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.res0) + off);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 r = r4[i];
+        uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { v[8 * i + 2 * e] += bf16_lo(w[e]); v[8 * i + 2 * e + 1] += bf16_hi(w[e]); }
+      }
+    }
+  }
+  if (p.res1 != nullptr) {
+    const uint4* r4 = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.res1) + off);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint4 r = r4[i];
+      uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { v[8 * i + 2 * e] += bf16_lo(w[e]); v[8 * i + 2 * e + 1] += bf16_hi(w[e]); }
+    }
+  }
+  // ---- secondary output: relu(v) in bf16 (input of the next 3x3 conv of a residual unit)
+  if (p.out1 != nullptr) {
+    uint4* o4 = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out1) + off);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint4 o;
+      o.x = pack_bf16(fmaxf(v[8 * i + 0], 0.f), fmaxf(v[8 * i + 1], 0.f));
+      o.y = pack_bf16(fmaxf(v[8 * i + 2], 0.f), fmaxf(v[8 * i + 3], 0.f));
+      o.z = pack_bf16(fmaxf(v[8 * i + 4], 0.f), fmaxf(v[8 * i + 5], 0.f));
+      o.w = pack_bf16(fmaxf(v[8 * i + 6], 0.f), fmaxf(v[8 * i + 7], 0.f));
+      o4[i] = o;
+    }
+  }
+  if (p.out0 == nullptr) return;
+  // ---- activation of the primary output
+  if (p.act == ACT_RELU) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+  } else if (p.act == ACT_GELU) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+  }
+  // ---- primary store (optionally column-split into two buffers: q | kv)
+  void* base = p.out0;
+  size_t o = off;
+  if (p.split_col > 0 && col0 >= p.split_col) {
+    base = p.out0b;
+    o = static_cast<size_t>(m) * p.ldo_b + (col0 - p.split_col);
+  }
+  if (p.out0_f32) {
+    float4* o4 = reinterpret_cast<float4*>(static_cast<float*>(base) + o);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  } else {
+    uint4* o4 = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(base) + o);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint4 q;
+      q.x = pack_bf16(v[8 * i + 0], v[8 * i + 1]);
+      q.y = pack_bf16(v[8 * i + 2], v[8 * i + 3]);
+      q.z = pack_bf16(v[8 * i + 4], v[8 * i + 5]);
+      q.w = pack_bf16(v[8 * i + 6], v[8 * i + 7]);
+      o4[i] = q;
+    }
+  }
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+            const __grid_constant__ GemmArgs p) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + Cfg::kStages * Cfg::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + Cfg::kStages;
+  uint64_t* tmem_full = bars + 2 * Cfg::kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int k_chunks = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const int k_iters = p.taps * k_chunks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int mt = tile / p.num_n_tiles, nt = tile % p.num_n_tiles;
+        const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, img = mt / (p.tiles_x * p.tiles_y);
+        const int x0 = tx * p.bw, y0 = ty * p.bh, n0 = nt * BLOCK_N;
+        for (int it = 0; it < k_iters; ++it) {
+          const int tap = it / k_chunks, kc = it % k_chunks;
+          int dy = 0, dx = 0;
+          if (p.taps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          tma_load_4d(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], kc * BLOCK_K, x0 + dx, y0 + dy, img);
+          tma_load_3d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kc * BLOCK_K, tap, n0);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, 0, 0);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int it = 0; it < k_iters; ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t a_desc = make_smem_desc_sw128(smem_u32(smem_a + stage * Cfg::kABytes), 1);
+          const uint64_t b_desc = make_smem_desc_sw128(smem_u32(smem_b + stage * Cfg::kBBytes), 1);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 16; ++k) {
+            // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (addr >> 4) field
+            umma_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem stage once the MMAs above have read it
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);  // accumulator ready for the epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue warps (TMEM -> regs -> global) =====================
+    const int quarter = warp & 3;            // TMEM lane quarter this warp may access
+    const int r = quarter * 32 + lane;       // row inside the 128-row tile
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int mt = tile / p.num_n_tiles, nt = tile % p.num_n_tiles;
+      const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, img = mt / (p.tiles_x * p.tiles_y);
+      const int px = tx * p.bw + r % p.bw, py = ty * p.bh + r / p.bw;
+      const bool row_ok = (px < p.W) && (py < p.H);
+      const int m = (img * p.H + py) * p.W + px;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      float fin[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        const int col0 = nt * BLOCK_N + c * 32;
+        if (col0 >= p.N) break;
+        uint32_t raw[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N + c * 32, raw);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+        epilogue_chunk<BLOCK_N>(p, v, m, col0, row_ok, img, py, px, fin);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (p.epi == EPI_FINAL && row_ok) {
+        // postprocess (fast3r/dust3r/heads/postprocess.py:16-64): pts = xyz/|xyz| * expm1(|xyz|), conf = 1+exp(c)
+        const float x = fin[0] + __ldg(p.b4 + 0), y = fin[1] + __ldg(p.b4 + 1), z = fin[2] + __ldg(p.b4 + 2);
+        const float c = fin[3] + __ldg(p.b4 + 3);
+        const float d = sqrtf(x * x + y * y + z * z);
+        const float s = expm1f(d) / fmaxf(d, 1e-8f);
+        float* pt = p.pts + static_cast<size_t>(m) * 3;
+        pt[0] = x * s; pt[1] = y * s; pt[2] = z * s;
+        p.conf[m] = 1.f + expf(c);
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+template <int BLOCK_N>
+static cudaError_t launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, int num_sms,
+                                 cudaStream_t stream) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int tiles = a.num_m_tiles * a.num_n_tiles;
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  gemm_kernel<BLOCK_N><<<grid, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(ta, tb, a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gemm(int block_n, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, int num_sms,
+                        cudaStream_t stream) {
+  if (block_n == 256) return launch_gemm_t<256>(ta, tb, a, num_sms, stream);
+  return launch_gemm_t<128>(ta, tb, a, num_sms, stream);
+}
+
+}  // namespace f3r

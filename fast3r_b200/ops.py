@@ -1,0 +1,128 @@
+"""Torch-tensor wrappers over the C ABI.  torch is plumbing here (device memory + streams); every op below
+is one call into libfast3r_b200.so on ``torch.cuda.current_stream()``.  No op has a PyTorch fallback."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import lib as L
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("fast3r_b200 ops need CUDA tensors (there is no CPU path)")
+    return t.data_ptr()
+
+
+def _chk(t: torch.Tensor, dtype, name: str):
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name}: must be contiguous")
+
+
+def gemm(a: torch.Tensor, wt: torch.Tensor, *, w: int, h: int = 1, nb: int = 1, taps: int = 1,
+         bias: Optional[torch.Tensor] = None, out0: Optional[torch.Tensor] = None,
+         out1: Optional[torch.Tensor] = None, res0: Optional[torch.Tensor] = None,
+         res1: Optional[torch.Tensor] = None, act: int = L.ACT_NONE, epi: int = L.EPI_STORE,
+         ldo: Optional[int] = None, split_col: int = 0, out0b: Optional[torch.Tensor] = None, ldo_b: int = 0,
+         tok_per_img: int = 0, grid_w: int = 0, rope_cols: int = 0, rope_cos=None, rope_sin=None,
+         emb_table=None, emb_ids=None, ct_k: int = 0, ct_cout: int = 0, w4=None, b4=None, pts=None, conf=None):
+    """Fused GEMM / implicit conv (f3r_gemm).  a: bf16 (..., K) channels-last with nb*h*w pixels;
+    wt: bf16 (N, taps, K)."""
+    _chk(a, BF16, "a"); _chk(wt, BF16, "wt")
+    n, k = wt.shape[0], wt.shape[-1]
+    assert wt.numel() == n * taps * k
+    assert a.shape[-1] == k and a.numel() == nb * h * w * k, (a.shape, nb, h, w, k)
+    d = L.GemmDesc()
+    d.a, d.wt = _ptr(a), _ptr(wt)
+    d.n, d.k, d.taps = n, k, taps
+    d.w, d.h, d.nb = w, h, nb
+    d.a_ld = k
+    d.epi, d.act = epi, act
+    d.ldo = ldo if ldo is not None else (ct_cout if epi == L.EPI_CONVT else n)
+    d.split_col, d.ldo_b = split_col, ldo_b
+    d.tok_per_img, d.grid_w, d.rope_cols = tok_per_img, grid_w, rope_cols
+    d.ct_k, d.ct_cout = ct_k, ct_cout
+    if bias is not None:
+        _chk(bias, F32, "bias")
+    d.bias = _ptr(bias)
+    if res0 is not None:
+        assert res0.dtype in (BF16, F32) and res0.is_contiguous()
+        d.res0_f32 = int(res0.dtype == F32)
+    d.res0 = _ptr(res0)
+    if res1 is not None:
+        _chk(res1, BF16, "res1")
+    d.res1 = _ptr(res1)
+    if out0 is not None:
+        assert out0.dtype in (BF16, F32) and out0.is_contiguous()
+        d.out0_f32 = int(out0.dtype == F32)
+    d.out0 = _ptr(out0)
+    if out0b is not None:
+        assert out0 is not None and out0b.dtype == out0.dtype
+    d.out0b = _ptr(out0b)
+    if out1 is not None:
+        _chk(out1, BF16, "out1")
+    d.out1 = _ptr(out1)
+    d.rope_cos, d.rope_sin = _ptr(rope_cos), _ptr(rope_sin)
+    d.emb_table, d.emb_ids = _ptr(emb_table), _ptr(emb_ids)
+    d.w4, d.b4, d.pts, d.conf = _ptr(w4), _ptr(b4), _ptr(pts), _ptr(conf)
+    L.check(L.load().f3r_gemm(C.byref(d), _stream()), "f3r_gemm")
+
+
+def linear(a: torch.Tensor, wt: torch.Tensor, bias=None, **kw):
+    """y = a @ wt.T (+bias ...) for a bf16 (M, K), wt bf16 (N, K)."""
+    return gemm(a, wt, w=a.numel() // a.shape[-1], bias=bias, **kw)
+
+
+def attention(q: torch.Tensor, kv: torch.Tensor, out: torch.Tensor, *, batch: int, heads: int, sq: int, skv: int,
+              scale: float, lse: Optional[torch.Tensor] = None):
+    """q (batch*sq, ldq) bf16, kv (batch*skv, ldkv) bf16 [K | V], out (batch*sq, ldo) bf16."""
+    _chk(q, BF16, "q"); _chk(kv, BF16, "kv"); _chk(out, BF16, "out")
+    ldq, ldkv, ldo = q.shape[-1], kv.shape[-1], out.shape[-1]
+    assert q.numel() == batch * sq * ldq and kv.numel() == batch * skv * ldkv and out.numel() == batch * sq * ldo
+    L.check(L.load().f3r_attention(_ptr(q), ldq, _ptr(kv), ldkv, _ptr(out), ldo, _ptr(lse), batch, heads, sq, skv,
+                                   float(scale), _stream()), "f3r_attention")
+
+
+def layernorm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float, out: torch.Tensor):
+    _chk(x, F32, "x"); _chk(w, F32, "w"); _chk(b, F32, "b")
+    assert out.dtype in (BF16, F32) and out.is_contiguous() and out.numel() == x.numel()
+    dim = x.shape[-1]
+    L.check(L.load().f3r_layernorm(_ptr(x), _ptr(w), _ptr(b), _ptr(out), int(out.dtype == F32), x.numel() // dim,
+                                   dim, float(eps), _stream()), "f3r_layernorm")
+
+
+def im2col_patch(img: torch.Tensor, out: torch.Tensor):
+    _chk(img, F32, "img"); _chk(out, BF16, "out")
+    n, c, h, w = img.shape
+    assert c == 3 and out.numel() == n * (h // 16) * (w // 16) * 768
+    L.check(L.load().f3r_im2col_patch(_ptr(img), _ptr(out), n, h, w, _stream()), "f3r_im2col_patch")
+
+
+def im2col3x3s2(x: torch.Tensor, out: torch.Tensor, n: int, h: int, w: int, c: int, ho: int, wo: int):
+    _chk(x, BF16, "x"); _chk(out, BF16, "out")
+    assert x.numel() == n * h * w * c and out.numel() == n * ho * wo * 9 * c
+    L.check(L.load().f3r_im2col3x3s2(_ptr(x), _ptr(out), n, h, w, c, ho, wo, _stream()), "f3r_im2col3x3s2")
+
+
+def upsample2x(x: torch.Tensor, out: torch.Tensor, n: int, h: int, w: int, c: int, ho: int, wo: int):
+    _chk(x, BF16, "x"); _chk(out, BF16, "out")
+    assert x.numel() == n * h * w * c and out.numel() == n * ho * wo * c
+    L.check(L.load().f3r_upsample2x(_ptr(x), _ptr(out), n, h, w, c, ho, wo, _stream()), "f3r_upsample2x")
+
+
+def cast_bf16(x: torch.Tensor, out: torch.Tensor):
+    _chk(x, F32, "x"); _chk(out, BF16, "out")
+    assert x.numel() == out.numel()
+    L.check(L.load().f3r_cast_bf16(_ptr(x), _ptr(out), x.numel(), _stream()), "f3r_cast_bf16")

@@ -1,0 +1,102 @@
+/* fast3r_b200 — C ABI of the B200-native Fast3R forward-pass kernels (libfast3r_b200.so).
+ *
+ * Drop-in boundary for the single-forward-pass hot path of facebookresearch/fast3r
+ * (CroCo encoder -> fusion decoder -> DPT heads).  The reference's only native precedent is the
+ * `curope` torch extension (fast3r/croco/models/curope/curope.cpp:54-59, kernels.cu:84-108): free functions
+ * over caller-owned device buffers, default/current stream, no ownership transfer, errors reported to Python
+ * as RuntimeError.  This ABI keeps those conventions but is torch-free: plain pointers, sizes and a
+ * cudaStream_t (passed as void*).  Every entry point
+ *   - works on caller-owned DEVICE pointers (16-byte aligned), never allocates or synchronises,
+ *   - enqueues on the given stream and returns 0 on success, non-zero on error (text via f3r_last_error()),
+ *   - is reentrant per thread (one Python thread per GPU/process, like the reference).
+ *
+ * Layout conventions: activations are row-major "channels-last": a token / pixel is a row; bf16 unless noted.
+ * Weights are bf16 [N_out, taps, K_in] (K contiguous); nn.Linear.weight (out,in) is already that with taps=1;
+ * nn.Conv2d.weight (out,in,kh,kw) must be permuted to (out, kh*kw, in); ConvTranspose2d (in,out,k,k) to
+ * ((i*k+j)*out + o, in).
+ */
+#ifndef FAST3R_B200_H
+#define FAST3R_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define F3R_ABI_VERSION 1
+
+/* epilogue kinds of f3r_gemm */
+enum { F3R_EPI_STORE = 0, F3R_EPI_ROPE = 1, F3R_EPI_IDXEMB = 2, F3R_EPI_CONVT = 3, F3R_EPI_FINAL = 4 };
+enum { F3R_ACT_NONE = 0, F3R_ACT_RELU = 1, F3R_ACT_GELU = 2 };
+
+/* One fused GEMM / implicit-GEMM convolution:
+ *   acc[m, n] = sum_{tap, k} A[pixel(m) + shift(tap), k] * Wt[n, tap, k]          (fp32 accumulation in TMEM)
+ *   v = acc + bias[n] (+ RoPE2D | + idx-embedding row) (+ res0[m,n]) (+ res1[m,n])
+ *   out1[m,n] = bf16(relu(v))   (optional);   out0[m,n] = act(v) as bf16 or fp32 (optional)
+ * Replaces: nn.Linear qkv/proj/fc1/fc2 (fast3r/croco/models/blocks.py:94-97,125-128), decoder_embed + image-index
+ * embedding add (fast3r/models/fast3r.py:782-799), RoPE2D on q,k (fast3r/croco/models/pos_embed.py:162-183),
+ * patch-embed conv (blocks.py:412-414), every Conv2d/ConvTranspose2d of the DPT head
+ * (fast3r/croco/models/dpt_block.py:42-77,105-123,187-195,367-381,416-481) and, with F3R_EPI_FINAL, the last
+ * ReLU + conv1x1 + postprocess (dpt_block.py:378-381, fast3r/dust3r/heads/postprocess.py:16-64). */
+typedef struct f3r_gemm_desc {
+  const void* a;       /* bf16 activation, viewed as (nb, h, w, c) with pixel stride a_ld elements            */
+  const void* wt;      /* bf16 weights [n, taps, k]                                                            */
+  int32_t n, k, taps;  /* taps: 1 (linear / 1x1) or 9 (3x3, stride 1, zero pad 1)                              */
+  int32_t w, h, nb;    /* spatial extent of A; a linear layer over M rows is (w=M, h=1, nb=1)                  */
+  int32_t a_ld;        /* elements between consecutive pixels of A (>= k)                                      */
+  int32_t epi, act;
+  int32_t out0_f32, res0_f32;
+  int32_t ldo;         /* row stride (elements) of out0 / out1 / res0 / res1                                   */
+  int32_t split_col, ldo_b; /* columns >= split_col of out0 go to out0b (row stride ldo_b); 0 disables         */
+  int32_t tok_per_img, grid_w, rope_cols; /* ROPE: tokens per image, patch-grid width, #leading columns rotated;
+                                             IDXEMB: tok_per_img tokens share emb_ids[m / tok_per_img]         */
+  int32_t ct_k, ct_cout;                  /* CONVT: kernel==stride k, out channels; n == k*k*ct_cout           */
+  const float* bias;   /* [n] (CONVT: [ct_cout]) or NULL                                                       */
+  const void* res0;    /* fp32 or bf16 [M, ldo] or NULL (may alias out0: in-place residual stream update)      */
+  const void* res1;    /* bf16 [M, ldo] or NULL                                                                */
+  void* out0;
+  void* out0b;
+  void* out1;
+  const float* rope_cos; /* [max_pos, 16] cos(pos * base^(-j/16))                                              */
+  const float* rope_sin;
+  const float* emb_table; /* fp32 [1000, n]                                                                    */
+  const int32_t* emb_ids; /* int32 [M / tok_per_img]                                                           */
+  const float* w4;     /* FINAL: fp32 [4, n] 1x1 conv weight, b4 fp32 [4]                                      */
+  const float* b4;
+  float* pts;          /* FINAL: fp32 [M, 3]                                                                   */
+  float* conf;         /* FINAL: fp32 [M]                                                                      */
+} f3r_gemm_desc;
+
+const char* f3r_last_error(void);
+int f3r_abi_version(void);
+/* Number of kernels launched through this library by the calling process so far. */
+uint64_t f3r_launch_count(void);
+
+int f3r_gemm(const f3r_gemm_desc* d, void* stream);
+
+/* softmax(scale * Q K^T) V per (batch, head), head_dim 64, non-causal (blocks.py:135-194).
+ * q: bf16 [batch, sq, ldq] (head h at columns h*64); kv: bf16 [batch, skv, ldkv] with K of head h at columns
+ * h*64 and V at columns heads*64 + h*64; out: bf16 [batch, sq, ldo].  lse (optional): fp32 [batch, heads, sq]. */
+int f3r_attention(const void* q, int32_t ldq, const void* kv, int32_t ldkv, void* out, int32_t ldo, float* lse,
+                  int32_t batch, int32_t heads, int32_t sq, int32_t skv, float scale, void* stream);
+
+/* nn.LayerNorm over the last dim of fp32 x [rows, dim] -> bf16 (or fp32) out  (blocks.py:219,228; fast3r.py:558,805) */
+int f3r_layernorm(const float* x, const float* w, const float* b, void* out, int32_t out_f32, int32_t rows,
+                  int32_t dim, float eps, void* stream);
+/* fp32 image batch (n,3,H,W) -> bf16 [n*(H/16)*(W/16), 768] patch rows (im2col of blocks.py:412 Conv2d k=s=16) */
+int f3r_im2col_patch(const float* img, void* out, int32_t n, int32_t h, int32_t w, void* stream);
+/* bf16 NHWC (n,h,w,c) -> bf16 [n*ho*wo, 9*c] for the 3x3 stride-2 pad-1 conv (dpt_block.py:471-478) */
+int f3r_im2col3x3s2(const void* in, void* out, int32_t n, int32_t h, int32_t w, int32_t c, int32_t ho, int32_t wo,
+                    void* stream);
+/* bilinear x2 align_corners=True on bf16 NHWC; writes the top-left (ho, wo) window of the (2h, 2w) result
+ * (dpt_block.py:234-247,374; crop of dpt_head.py:69-71) */
+int f3r_upsample2x(const void* in, void* out, int32_t n, int32_t h, int32_t w, int32_t c, int32_t ho, int32_t wo,
+                   void* stream);
+/* fp32 -> bf16, count multiple of 4 */
+int f3r_cast_bf16(const float* in, void* out, size_t count, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
