@@ -77,6 +77,7 @@ extern "C" {
 
 const char* f3r_last_error(void) { return g_err; }
 int f3r_abi_version(void) { return F3R_ABI_VERSION; }
+size_t f3r_gemm_desc_size(void) { return sizeof(f3r_gemm_desc); }
 uint64_t f3r_launch_count(void) { return g_launches.load(); }
 
 int f3r_gemm(const f3r_gemm_desc* d, void* stream) {

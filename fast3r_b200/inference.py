@@ -1,0 +1,112 @@
+"""Drop-in for ``fast3r.dust3r.inference_multiview`` (reference: fast3r/dust3r/inference_multiview.py:22-104,
+collation helpers fast3r/dust3r/utils/device.py:52-95).  Same signatures, same result structure
+``{"views": [...], "preds": [...], "loss": None}`` moved to CPU, same optional ``profiling_info``.
+
+Precision mapping: the reference only disables autocast for the *string* "32"; any other value
+selects an autocast dtype.  This implementation has ONE numeric path (bf16 tensor-core operands, fp32
+accumulation / residual stream / statistics, fp32 outputs), which is at least as close to the reference's fp32
+result as the reference's own bf16-autocast path, so every ``dtype`` value maps onto it and preds come back fp32.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+_MOVE_KEYS = "img pts3d valid_mask camera_pose camera_intrinsics F_matrix corres".split()
+
+
+def todevice(batch, device, callback=None, non_blocking=False):
+    """fast3r/dust3r/utils/device.py:14-49."""
+    if callback:
+        batch = callback(batch)
+    if isinstance(batch, dict):
+        return {k: todevice(v, device) for k, v in batch.items()}
+    if isinstance(batch, (tuple, list)):
+        return type(batch)(todevice(x, device) for x in batch)
+    x = batch
+    if device == "numpy":
+        if isinstance(x, torch.Tensor):
+            x = x.detach().cpu().numpy()
+    elif x is not None:
+        if isinstance(x, np.ndarray):
+            x = torch.from_numpy(x)
+        if torch.is_tensor(x):
+            x = x.to(device, non_blocking=non_blocking)
+    return x
+
+
+def to_cpu(x):
+    return todevice(x, "cpu")
+
+
+def listify(elems):
+    return [x for e in elems for x in e]
+
+
+def collate_with_cat(whatever, lists=False):
+    """fast3r/dust3r/utils/device.py:60-91."""
+    if isinstance(whatever, dict):
+        return {k: collate_with_cat(vals, lists=lists) for k, vals in whatever.items()}
+    elif isinstance(whatever, (tuple, list)):
+        if len(whatever) == 0:
+            return whatever
+        elem = whatever[0]
+        T = type(whatever)
+        if elem is None:
+            return None
+        if isinstance(elem, (bool, float, int, str)):
+            return whatever
+        if isinstance(elem, tuple):
+            return T(collate_with_cat(x, lists=lists) for x in zip(*whatever))
+        if isinstance(elem, dict):
+            return {k: collate_with_cat([e[k] for e in whatever], lists=lists) for k in elem}
+        if isinstance(elem, torch.Tensor):
+            return listify(whatever) if lists else torch.cat(whatever)
+        if isinstance(elem, np.ndarray):
+            return listify(whatever) if lists else torch.cat([torch.from_numpy(x) for x in whatever])
+        return sum(whatever, T())
+
+
+def check_if_same_size(imgs):
+    shapes = [img["img"].shape[-2:] for img in imgs]
+    return all(shape == shapes[0] for shape in shapes)
+
+
+def loss_of_one_batch(batch, model, criterion, device, precision, symmetrize_batch=False, use_amp=False, ret=None,
+                      profiling=False):
+    """fast3r/dust3r/inference_multiview.py:22-67 (H2D of the view tensors, model call, optional criterion)."""
+    device = torch.device(device)
+    for view in batch:
+        for name in _MOVE_KEYS:
+            if name not in view:
+                continue
+            view[name] = view[name].to(device, non_blocking=True)
+    views = batch
+    if profiling:
+        preds, profiling_info = model(views, profiling=profiling)
+    else:
+        preds = model(views, profiling=profiling)
+    loss = criterion(views, preds) if criterion is not None else None
+    result = dict(views=views, preds=preds, loss=loss)
+    if profiling:
+        result["profiling_info"] = profiling_info
+    return result[ret] if ret else result
+
+
+@torch.no_grad()
+def inference(multiple_views_in_one_sample, model, device, dtype, verbose=True, profiling=False):
+    """fast3r/dust3r/inference_multiview.py:70-99."""
+    if verbose:
+        print(f">> Inference with model on {len(multiple_views_in_one_sample)} images")
+    result = []
+    multiple_shapes = not check_if_same_size(multiple_views_in_one_sample)
+    res = loss_of_one_batch(collate_with_cat([tuple(multiple_views_in_one_sample)]), model, None, device, dtype,
+                            profiling=profiling)
+    profiling_info = None
+    if profiling and "profiling_info" in res:
+        profiling_info = res.pop("profiling_info")
+    result.append(to_cpu(res))
+    result = collate_with_cat(result, lists=multiple_shapes)
+    if profiling and profiling_info is not None:
+        return result, profiling_info
+    return result

@@ -36,7 +36,7 @@ class GemmDesc(C.Structure):
     ]
 
 
-EXPORTS = ["f3r_last_error", "f3r_abi_version", "f3r_launch_count", "f3r_gemm", "f3r_attention", "f3r_layernorm",
+EXPORTS = ["f3r_last_error", "f3r_abi_version", "f3r_gemm_desc_size", "f3r_launch_count", "f3r_gemm", "f3r_attention", "f3r_layernorm",
            "f3r_im2col_patch", "f3r_im2col3x3s2", "f3r_upsample2x", "f3r_cast_bf16"]
 
 _lib = None
@@ -69,8 +69,9 @@ def load() -> C.CDLL:
     for name in ("f3r_gemm", "f3r_attention", "f3r_layernorm", "f3r_im2col_patch", "f3r_im2col3x3s2",
                  "f3r_upsample2x", "f3r_cast_bf16"):
         getattr(lib, name).restype = C.c_int
-    if lib.f3r_abi_version() != 1:
-        raise RuntimeError("libfast3r_b200.so ABI version mismatch")
+    lib.f3r_gemm_desc_size.restype = C.c_size_t
+    if lib.f3r_abi_version() != 1 or lib.f3r_gemm_desc_size() != C.sizeof(GemmDesc):
+        raise RuntimeError("libfast3r_b200.so ABI mismatch (rebuild: python -m fast3r_b200.build --force)")
     _lib = lib
     return lib
 

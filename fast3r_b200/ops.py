@@ -11,6 +11,11 @@ from . import lib as L
 
 BF16, F32 = torch.bfloat16, torch.float32
 
+# Optional per-launch CUDA-event timing of the dominant kernel (bench.py's live roofline measurement).
+# When set to a list, attention() appends (batch, heads, sq, skv, start_event, end_event), recorded on the
+# launching stream.
+KERNEL_TIMER = None
+
 
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
@@ -91,8 +96,15 @@ def attention(q: torch.Tensor, kv: torch.Tensor, out: torch.Tensor, *, batch: in
     _chk(q, BF16, "q"); _chk(kv, BF16, "kv"); _chk(out, BF16, "out")
     ldq, ldkv, ldo = q.shape[-1], kv.shape[-1], out.shape[-1]
     assert q.numel() == batch * sq * ldq and kv.numel() == batch * skv * ldkv and out.numel() == batch * sq * ldo
+    timer = KERNEL_TIMER
+    if timer is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     L.check(L.load().f3r_attention(_ptr(q), ldq, _ptr(kv), ldkv, _ptr(out), ldo, _ptr(lse), batch, heads, sq, skv,
                                    float(scale), _stream()), "f3r_attention")
+    if timer is not None:
+        e1.record()
+        timer.append((batch, heads, sq, skv, e0, e1))
 
 
 def layernorm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float, out: torch.Tensor):

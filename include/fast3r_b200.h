@@ -70,6 +70,8 @@ typedef struct f3r_gemm_desc {
 
 const char* f3r_last_error(void);
 int f3r_abi_version(void);
+/* sizeof(f3r_gemm_desc) as compiled into the library (binding-side struct layout guard). */
+size_t f3r_gemm_desc_size(void);
 /* Number of kernels launched through this library by the calling process so far. */
 uint64_t f3r_launch_count(void);
 
