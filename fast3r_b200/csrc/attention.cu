@@ -30,6 +30,23 @@ F3R_DEVICE float ex2_approx(float x) {
   return y;
 }
 
+// Blackwell packed fp32x2 / 3-input ALU ops (SASS FFMA2 / FADD2 / FMNMX3): halve the issue slots of the softmax.
+F3R_DEVICE float max3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+F3R_DEVICE void ffma2(float& d0, float& d1, float a0, float a1, float b, float c) {
+  asm("{ .reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%4}; mov.b64 rc, {%5,%5};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0,%1}, rd; }"
+      : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b), "f"(c));
+}
+F3R_DEVICE void fadd2(float& d0, float& d1, float a0, float a1) {
+  asm("{ .reg .b64 ra, rd; mov.b64 rd, {%0,%1}; mov.b64 ra, {%2,%3};\n\t"
+      "add.rn.f32x2 rd, rd, ra; mov.b64 {%0,%1}, rd; }"
+      : "+f"(d0), "+f"(d1) : "f"(a0), "f"(a1));
+}
+
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
                  const __grid_constant__ AttnArgs p) {
@@ -191,14 +208,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             if (i >= valid) s[i] = 0xff800000u;  // -inf
         }
       }
-      float mx0 = __uint_as_float(s[0]), mx1 = __uint_as_float(s[1]);
-      float mx2 = __uint_as_float(s[2]), mx3 = __uint_as_float(s[3]);
+      float mx0 = max3(__uint_as_float(s[0]), __uint_as_float(s[1]), __uint_as_float(s[2]));
+      float mx1 = max3(__uint_as_float(s[3]), __uint_as_float(s[4]), __uint_as_float(s[5]));
+      float mx2 = __uint_as_float(s[6]), mx3 = __uint_as_float(s[7]);
 #pragma unroll
-      for (int i = 4; i < 128; i += 4) {
-        mx0 = fmaxf(mx0, __uint_as_float(s[i]));
-        mx1 = fmaxf(mx1, __uint_as_float(s[i + 1]));
-        mx2 = fmaxf(mx2, __uint_as_float(s[i + 2]));
-        mx3 = fmaxf(mx3, __uint_as_float(s[i + 3]));
+      for (int i = 8; i < 128; i += 8) {
+        mx0 = max3(mx0, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
+        mx1 = max3(mx1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
+        mx2 = max3(mx2, __uint_as_float(s[i + 4]), __uint_as_float(s[i + 5]));
+        mx3 = max3(mx3, __uint_as_float(s[i + 6]), __uint_as_float(s[i + 7]));
       }
       const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
       // lazy rescale: move the reference only if the max grew by more than 8 (log2 domain)
@@ -228,11 +246,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       uint32_t pk[64];
 #pragma unroll
       for (int i = 0; i < 128; i += 4) {
-        const float e0 = ex2_approx(fmaf(__uint_as_float(s[i]), sl2, nm));
-        const float e1 = ex2_approx(fmaf(__uint_as_float(s[i + 1]), sl2, nm));
-        const float e2 = ex2_approx(fmaf(__uint_as_float(s[i + 2]), sl2, nm));
-        const float e3 = ex2_approx(fmaf(__uint_as_float(s[i + 3]), sl2, nm));
-        l0 += e0; l1 += e1; l2 += e2; l3 += e3;
+        float x0, x1, x2, x3;
+        ffma2(x0, x1, __uint_as_float(s[i]), __uint_as_float(s[i + 1]), sl2, nm);
+        ffma2(x2, x3, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]), sl2, nm);
+        const float e0 = ex2_approx(x0), e1 = ex2_approx(x1), e2 = ex2_approx(x2), e3 = ex2_approx(x3);
+        fadd2(l0, l1, e0, e1);
+        fadd2(l2, l3, e2, e3);
         pk[i / 2] = pack_bf16(e0, e1);
         pk[i / 2 + 1] = pack_bf16(e2, e3);
       }
