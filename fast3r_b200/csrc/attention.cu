@@ -12,15 +12,18 @@
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread), warps 4-7 = softmax of tile 0,
 // warps 8-11 = softmax of tile 1 (one thread per query row).  setmaxnreg moves registers from warpgroup 0
 // to the softmax warpgroups, which keep a whole 128-wide score row in registers.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "f3r_kernels.h"
 
 namespace f3r {
 
-constexpr int ATT_THREADS = 384;  // warpgroup 0: TMA + MMA (+2 idle warps), warpgroups 1/2: softmax of tile 0/1
+// kSplit = threads per query row in the softmax (1: 8 softmax warps, 2: 16 softmax warps, better latency hiding)
+template <int kSplit> constexpr int att_threads() { return 128 + 256 * kSplit; }  // warpgroup 0: TMA + MMA (+2 idle)
 constexpr int ATT_STAGES = 4;
 constexpr int ATT_TILE_BYTES = 128 * 64 * 2;  // 16 KB: 128 rows x 64 bf16
-constexpr int ATT_SMEM_BYTES = (2 + 2 * ATT_STAGES) * ATT_TILE_BYTES + 1024 + 256;
+constexpr int ATT_SMEM_BYTES = (2 + 2 * ATT_STAGES) * ATT_TILE_BYTES + 1024 + 256 + 4096 /*row-max exchange*/;
 
 constexpr uint32_t TM_S0 = 0, TM_S1 = 128, TM_P0 = 256, TM_P1 = 320, TM_O0 = 384, TM_O1 = 448;
 
@@ -47,7 +50,8 @@ F3R_DEVICE void fadd2(float& d0, float& d1, float a0, float a1) {
       : "+f"(d0), "+f"(d1) : "f"(a0), "f"(a1));
 }
 
-__global__ void __launch_bounds__(ATT_THREADS, 1)
+template <int kSplit>
+__global__ void __launch_bounds__(att_threads<kSplit>(), 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
                  const __grid_constant__ AttnArgs p) {
   extern __shared__ uint8_t smem_raw[];
@@ -66,6 +70,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   uint64_t* p_full = s_free + 2;                 // 2
   uint64_t* pv_done = p_full + 2;                // 2
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(pv_done + 2);
+  float* xbuf = reinterpret_cast<float*>(smem_v + ATT_STAGES * ATT_TILE_BYTES + 256);  // [tile][parity][half][128]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -86,8 +91,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
     }
     for (int t = 0; t < 2; ++t) {
-      mbar_init(&s_full[t], 1); mbar_init(&s_free[t], 128);
-      mbar_init(&p_full[t], 128); mbar_init(&pv_done[t], 1);
+      mbar_init(&s_full[t], 1); mbar_init(&s_free[t], 128 * kSplit);
+      mbar_init(&p_full[t], 128 * kSplit); mbar_init(&pv_done[t], 1);
     }
     fence_barrier_init();
   }
@@ -98,7 +103,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+    if constexpr (kSplit == 1) asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+    else asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
   if (warp == 0) {
     if (lane == 0) {
       // ===================== TMA producer =====================
@@ -176,35 +182,38 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   }
   } else {
     // ===================== softmax warps =====================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
-    const int t = (warp - 4) >> 2;        // query tile 0 / 1
-    const int quarter = warp & 3;         // TMEM lane quarter accessible to this warp
-    const int row = quarter * 32 + lane;  // row in the 128-row tile
+    if constexpr (kSplit == 1) asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    constexpr int COLS = 128 / kSplit;      // score columns per thread
+    constexpr int OCOLS = 64 / kSplit;      // output columns per thread
+    const int sw = warp - 4;
+    const int t = sw / (4 * kSplit);        // query tile 0 / 1
+    const int half = (sw >> 2) % kSplit;    // which column slice of the row this thread owns
+    const int quarter = warp & 3;           // TMEM lane quarter accessible to this warp
+    const int row = quarter * 32 + lane;    // row in the 128-row tile
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
-    const uint32_t tm_s = tmem_base + lane_base + (t ? TM_S1 : TM_S0);
-    const uint32_t tm_p = tmem_base + lane_base + (t ? TM_P1 : TM_P0);
-    const uint32_t tm_o = tmem_base + lane_base + (t ? TM_O1 : TM_O0);
+    const uint32_t tm_s = tmem_base + lane_base + (t ? TM_S1 : TM_S0) + half * COLS;
+    const uint32_t tm_p = tmem_base + lane_base + (t ? TM_P1 : TM_P0) + half * (COLS / 2);
+    const uint32_t tm_o = tmem_base + lane_base + (t ? TM_O1 : TM_O0) + half * OCOLS;
     const float sl2 = p.scale_log2;
     float m_used = -INFINITY;  // raw-score reference max the exponentials are taken against
-    float l = 0.f;
+    float l = 0.f;             // this thread's partial row sum
 
     for (int j = 0; j < nkv; ++j) {
       mbar_wait(&s_full[t], j & 1);
       tc_fence_after();
-      uint32_t s[128];
-      tmem_ld32(tm_s + 0, s + 0);
-      tmem_ld32(tm_s + 32, s + 32);
-      tmem_ld32(tm_s + 64, s + 64);
-      tmem_ld32(tm_s + 96, s + 96);
+      uint32_t s[COLS];
+#pragma unroll
+      for (int c = 0; c < COLS / 32; ++c) tmem_ld32(tm_s + 32 * c, s + 32 * c);
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&s_free[t]);  // S_t may be overwritten by the next QK^T
 
       if (j == nkv - 1) {
-        const int valid = p.skv - j * 128;
-        if (valid < 128) {
+        const int valid = p.skv - j * 128 - half * COLS;
+        if (valid < COLS) {
 #pragma unroll
-          for (int i = 0; i < 128; ++i)
+          for (int i = 0; i < COLS; ++i)
             if (i >= valid) s[i] = 0xff800000u;  // -inf
         }
       }
@@ -212,13 +221,20 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       float mx1 = max3(__uint_as_float(s[3]), __uint_as_float(s[4]), __uint_as_float(s[5]));
       float mx2 = __uint_as_float(s[6]), mx3 = __uint_as_float(s[7]);
 #pragma unroll
-      for (int i = 8; i < 128; i += 8) {
+      for (int i = 8; i < COLS; i += 8) {
         mx0 = max3(mx0, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
         mx1 = max3(mx1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
         mx2 = max3(mx2, __uint_as_float(s[i + 4]), __uint_as_float(s[i + 5]));
         mx3 = max3(mx3, __uint_as_float(s[i + 6]), __uint_as_float(s[i + 7]));
       }
-      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      if constexpr (kSplit == 2) {
+        // combine the two half-row maxima (both threads must take the same rescale decision)
+        float* xb = xbuf + ((t * 2 + (j & 1)) * 2) * 128;
+        xb[half * 128 + row] = mx;
+        asm volatile("bar.sync %0, 256;" ::"r"(1 + t) : "memory");
+        mx = fmaxf(mx, xb[(half ^ 1) * 128 + row]);
+      }
       // lazy rescale: move the reference only if the max grew by more than 8 (log2 domain)
       float alpha = 1.f;
       const bool need = (mx - m_used) * sl2 > 8.f;  // (-inf reference => true)
@@ -232,7 +248,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         tc_fence_after();
         uint32_t o[32];
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
+        for (int c = 0; c < OCOLS / 32; ++c) {
           tmem_ld32(tm_o + 32 * c, o);
           tmem_ld_wait();
 #pragma unroll
@@ -243,9 +259,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       }
       const float nm = -m_used * sl2;
       float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
-      uint32_t pk[64];
+      uint32_t pk[COLS / 2];
 #pragma unroll
-      for (int i = 0; i < 128; i += 4) {
+      for (int i = 0; i < COLS; i += 4) {
         float x0, x1, x2, x3;
         ffma2(x0, x1, __uint_as_float(s[i]), __uint_as_float(s[i + 1]), sl2, nm);
         ffma2(x2, x3, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]), sl2, nm);
@@ -260,21 +276,28 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         mbar_wait(&pv_done[t], (j - 1) & 1);  // previous PV has consumed P_t
         tc_fence_after();
       }
-      tmem_st32(tm_p + 0, pk);
-      tmem_st32(tm_p + 32, pk + 32);
+#pragma unroll
+      for (int c = 0; c < COLS / 64; ++c) tmem_st32(tm_p + 32 * c, pk + 32 * c);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&p_full[t]);
     }
 
     // ---- epilogue: O / l -> bf16 -> global
+    if constexpr (kSplit == 2) {
+      float* xb = xbuf + ((t * 2 + (nkv & 1)) * 2) * 128;  // slot not used by the last iteration's exchange
+      xb[half * 128 + row] = l;
+      asm volatile("bar.sync %0, 256;" ::"r"(1 + t) : "memory");
+      l += xb[(half ^ 1) * 128 + row];
+    }
     mbar_wait(&pv_done[t], (nkv - 1) & 1);
     tc_fence_after();
     const int q = qt * 256 + t * 128 + row;
     const float inv = 1.f / l;
-    __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.out) + (static_cast<size_t>(b) * p.sq + q) * p.ldo + h * 64;
+    __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.out) + (static_cast<size_t>(b) * p.sq + q) * p.ldo + h * 64 +
+                         half * OCOLS;
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
+    for (int c = 0; c < OCOLS / 32; ++c) {
       uint32_t o[32];
       tmem_ld32(tm_o + 32 * c, o);
       tmem_ld_wait();
@@ -291,7 +314,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         }
       }
     }
-    if (p.lse != nullptr && q < p.sq)
+    if (p.lse != nullptr && q < p.sq && half == 0)
       p.lse[(static_cast<size_t>(b) * p.heads + h) * p.sq + q] = m_used * sl2 * 0.69314718056f + logf(l);
   }
 
@@ -304,17 +327,28 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   }
 }
 
-cudaError_t launch_attention(const CUtensorMap& tq, const CUtensorMap& tkv, const AttnArgs& a, cudaStream_t stream) {
+template <int kSplit>
+static cudaError_t launch_attention_t(const CUtensorMap& tq, const CUtensorMap& tkv, const AttnArgs& a,
+                                      cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e =
-        cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(attention_kernel<kSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         ATT_SMEM_BYTES);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
   const int grid = a.batch * a.heads * a.q_tiles;
-  attention_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tq, tkv, a);
+  attention_kernel<kSplit><<<grid, att_threads<kSplit>(), ATT_SMEM_BYTES, stream>>>(tq, tkv, a);
   return cudaGetLastError();
+}
+
+cudaError_t launch_attention(const CUtensorMap& tq, const CUtensorMap& tkv, const AttnArgs& a, cudaStream_t stream) {
+  static int variant = -1;
+  if (variant < 0) {
+    const char* e = getenv("F3R_ATTN_SPLIT");
+    variant = (e && e[0] == '1') ? 1 : 2;
+  }
+  return variant == 1 ? launch_attention_t<1>(tq, tkv, a, stream) : launch_attention_t<2>(tq, tkv, a, stream);
 }
 
 }  // namespace f3r

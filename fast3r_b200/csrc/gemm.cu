@@ -18,7 +18,7 @@ namespace f3r {
 
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
-constexpr int GEMM_THREADS = 192;  // warp0 TMA, warp1 MMA(+TMEM alloc), warps 2-5 epilogue
+constexpr int GEMM_THREADS = 320;  // warp0 TMA, warp1 MMA(+TMEM alloc), warps 2-9 epilogue (2 per TMEM lane quarter)
 
 template <int BLOCK_N>
 struct GemmCfg {
@@ -26,13 +26,64 @@ struct GemmCfg {
   static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
   static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + 4096 /*FINAL partials*/;
   static constexpr uint32_t kTmemCols = 2 * BLOCK_N;
 };
 
+// Residual operands of one 32-column chunk, fetched ahead of the TMEM load they are added to.
+struct ResChunk {
+  uint4 r0[8];  // res0: 32 fp32 (8 x uint4) or 32 bf16 (first 4 x uint4)
+  uint4 r1[4];  // res1: 32 bf16
+};
+
+__device__ __forceinline__ size_t out_offset(const GemmArgs& p, int m, int col0, int img, int py, int px) {
+  if (p.epi == EPI_CONVT) {
+    const int ij = col0 / p.ct_cout, o0 = col0 % p.ct_cout, k = p.ct_k;
+    const int oy = py * k + ij / k, ox = px * k + ij % k;
+    return ((static_cast<size_t>(img) * p.H * k + oy) * (p.W * k) + ox) * p.ct_cout + o0;
+  }
+  return static_cast<size_t>(m) * p.ldo + col0;
+}
+
+__device__ __forceinline__ void prefetch_res(const GemmArgs& p, ResChunk& rc, size_t off, bool row_ok) {
+  if (!row_ok) return;
+  if (p.res0 != nullptr) {
+    if (p.res0_f32) {
+      const uint4* r4 = reinterpret_cast<const uint4*>(static_cast<const float*>(p.res0) + off);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) rc.r0[i] = r4[i];
+    } else {
+      const uint4* r4 = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.res0) + off);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) rc.r0[i] = r4[i];
+    }
+  }
+  if (p.res1 != nullptr) {
+    const uint4* r4 = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.res1) + off);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) rc.r1[i] = r4[i];
+  }
+}
+
+// exact-erf GELU (nn.GELU(), fast3r/croco/models/blocks.py:83) with erf from Abramowitz-Stegun 7.1.26
+// (|abs err| <= 1.5e-7, far below the bf16 rounding of the stored activation); 2 MUFU + ~12 FMA-class ops.
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  const float e = exp2f(-1.4426950408889634f * z * z);
+  const float erf_abs = fmaf(-poly, e, 1.0f);
+  const float erf_v = copysignf(erf_abs, x);
+  return 0.5f * x * (1.0f + erf_v);
+}
+
 template <int BLOCK_N>
-__device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, float (&v)[32], int m, int col0, bool row_ok,
-                                               int img, int py, int px, float (&fin)[4]) {
+__device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, float (&v)[32], const ResChunk& rc, int m, int col0,
+                                               bool row_ok, size_t off, float (&fin)[4]) {
   // ---- bias
   if (p.bias != nullptr) {
     const float4* b4 = reinterpret_cast<const float4*>(p.bias + (p.epi == EPI_CONVT ? (col0 % p.ct_cout) : col0));
@@ -84,40 +135,27 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, float (&v)[32]
     return;
   }
 
-  // ---- residual adds
-  size_t off;
-  if (p.epi == EPI_CONVT) {
-    const int ij = col0 / p.ct_cout, o0 = col0 % p.ct_cout, k = p.ct_k;
-    const int oy = py * k + ij / k, ox = px * k + ij % k;
-    off = ((static_cast<size_t>(img) * p.H * k + oy) * (p.W * k) + ox) * p.ct_cout + o0;
-  } else {
-    off = static_cast<size_t>(m) * p.ldo + col0;
-  }
+  // ---- residual adds (operands were prefetched)
   if (p.res0 != nullptr) {
     if (p.res0_f32) {
-      const float4* r4 = reinterpret_cast<const float4*>(static_cast<const float*>(p.res0) + off);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        float4 r = r4[i];
-        v[4 * i + 0] += r.x; v[4 * i + 1] += r.y; v[4 * i + 2] += r.z; v[4 * i + 3] += r.w;
+        v[4 * i + 0] += __uint_as_float(rc.r0[i].x); v[4 * i + 1] += __uint_as_float(rc.r0[i].y);
+        v[4 * i + 2] += __uint_as_float(rc.r0[i].z); v[4 * i + 3] += __uint_as_float(rc.r0[i].w);
       }
     } else {
-      const uint4* r4 = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.res0) + off);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        uint4 r = r4[i];
-        uint32_t w[4] = {r.x, r.y, r.z, r.w};
+        const uint32_t w[4] = {rc.r0[i].x, rc.r0[i].y, rc.r0[i].z, rc.r0[i].w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) { v[8 * i + 2 * e] += bf16_lo(w[e]); v[8 * i + 2 * e + 1] += bf16_hi(w[e]); }
       }
     }
   }
   if (p.res1 != nullptr) {
-    const uint4* r4 = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.res1) + off);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      uint4 r = r4[i];
-      uint32_t w[4] = {r.x, r.y, r.z, r.w};
+      const uint32_t w[4] = {rc.r1[i].x, rc.r1[i].y, rc.r1[i].z, rc.r1[i].w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) { v[8 * i + 2 * e] += bf16_lo(w[e]); v[8 * i + 2 * e + 1] += bf16_hi(w[e]); }
     }
@@ -142,7 +180,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, float (&v)[32]
     for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
   } else if (p.act == ACT_GELU) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+    for (int i = 0; i < 32; ++i) v[i] = gelu_fast(v[i]);
   }
   // ---- primary store (optionally column-split into two buffers: q | kv)
   void* base = p.out0;
@@ -184,6 +222,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   uint64_t* tmem_full = bars + 2 * Cfg::kStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* fin_smem = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + 256);  // [2][128][4]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -192,7 +231,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
     for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 8); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_ptr);
@@ -254,8 +293,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
   } else {
     // ===================== epilogue warps (TMEM -> regs -> global) =====================
+    // Two warps per TMEM lane quarter: warp (2+q') and (6+q') take the even / odd 32-column chunks of the tile.
     const int quarter = warp & 3;            // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;        // 0: even chunks, 1: odd chunks
     const int r = quarter * 32 + lane;       // row inside the 128-row tile
+    constexpr int kChunks = BLOCK_N / 32;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int mt = tile / p.num_n_tiles, nt = tile % p.num_n_tiles;
@@ -263,33 +305,51 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       const int px = tx * p.bw + r % p.bw, py = ty * p.bh + r / p.bw;
       const bool row_ok = (px < p.W) && (py < p.H);
       const int m = (img * p.H + py) * p.W + px;
+      const int n_valid = min(kChunks, (p.N - nt * BLOCK_N + 31) / 32);
+      ResChunk rc_cur, rc_next;
+      size_t off_cur = 0, off_next = 0;
+      if (half < n_valid) {  // residual operands of the first chunk are fetched while the MMAs still run
+        off_next = out_offset(p, m, nt * BLOCK_N + half * 32, img, py, px);
+        prefetch_res(p, rc_next, off_next, row_ok);
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       float fin[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
+      for (int c = half; c < n_valid; c += 2) {
         const int col0 = nt * BLOCK_N + c * 32;
-        if (col0 >= p.N) break;
         uint32_t raw[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N + c * 32, raw);
+        rc_cur = rc_next;
+        off_cur = off_next;
+        if (c + 2 < n_valid) {
+          off_next = out_offset(p, m, col0 + 64, img, py, px);
+          prefetch_res(p, rc_next, off_next, row_ok);
+        }
         tmem_ld_wait();
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
-        epilogue_chunk<BLOCK_N>(p, v, m, col0, row_ok, img, py, px, fin);
+        epilogue_chunk<BLOCK_N>(p, v, rc_cur, m, col0, row_ok, off_cur, fin);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-      if (p.epi == EPI_FINAL && row_ok) {
-        // postprocess (fast3r/dust3r/heads/postprocess.py:16-64): pts = xyz/|xyz| * expm1(|xyz|), conf = 1+exp(c)
-        const float x = fin[0] + __ldg(p.b4 + 0), y = fin[1] + __ldg(p.b4 + 1), z = fin[2] + __ldg(p.b4 + 2);
-        const float c = fin[3] + __ldg(p.b4 + 3);
-        const float d = sqrtf(x * x + y * y + z * z);
-        const float s = expm1f(d) / fmaxf(d, 1e-8f);
-        float* pt = p.pts + static_cast<size_t>(m) * 3;
-        pt[0] = x * s; pt[1] = y * s; pt[2] = z * s;
-        p.conf[m] = 1.f + expf(c);
+      if (p.epi == EPI_FINAL) {
+        // combine the two half-row partial dot products, then postprocess
+        // (fast3r/dust3r/heads/postprocess.py:16-64): pts = xyz/|xyz| * expm1(|xyz|), conf = 1+exp(c)
+        float* slot = fin_smem + (acc * 128 + r) * 4;
+        if (half == 1) { slot[0] = fin[0]; slot[1] = fin[1]; slot[2] = fin[2]; slot[3] = fin[3]; }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (half == 0 && row_ok) {
+          const float x = fin[0] + slot[0] + __ldg(p.b4 + 0), y = fin[1] + slot[1] + __ldg(p.b4 + 1);
+          const float z = fin[2] + slot[2] + __ldg(p.b4 + 2), c = fin[3] + slot[3] + __ldg(p.b4 + 3);
+          const float d = sqrtf(x * x + y * y + z * z);
+          const float sc = expm1f(d) / fmaxf(d, 1e-8f);
+          float* pt = p.pts + static_cast<size_t>(m) * 3;
+          pt[0] = x * sc; pt[1] = y * sc; pt[2] = z * sc;
+          p.conf[m] = 1.f + expf(c);
+        }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
