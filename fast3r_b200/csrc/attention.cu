@@ -103,8 +103,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp < 4) {
+    // register budget (must balance inside the CTA's launch allocation):
+    //   kSplit 1: 384 thr x 168 = 64512 = 128 x 72 + 256 x 216      kSplit 2: 640 thr x 96 = 61440 = 128 x 64 + 512 x 104
     if constexpr (kSplit == 1) asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
-    else asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+    else asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
   if (warp == 0) {
     if (lane == 0) {
       // ===================== TMA producer =====================
@@ -345,8 +347,10 @@ static cudaError_t launch_attention_t(const CUtensorMap& tq, const CUtensorMap& 
 cudaError_t launch_attention(const CUtensorMap& tq, const CUtensorMap& tkv, const AttnArgs& a, cudaStream_t stream) {
   static int variant = -1;
   if (variant < 0) {
+    // default: one thread per score row (measured 2.68 ms vs 3.11 ms per decoder layer at N=32 for the
+    // two-threads-per-row variant, profiles/r01_notes.md); F3R_ATTN_SPLIT=2 selects the latter for experiments
     const char* e = getenv("F3R_ATTN_SPLIT");
-    variant = (e && e[0] == '1') ? 1 : 2;
+    variant = (e && e[0] == '2') ? 2 : 1;
   }
   return variant == 1 ? launch_attention_t<1>(tq, tkv, a, stream) : launch_attention_t<2>(tq, tkv, a, stream);
 }

@@ -37,16 +37,17 @@ def main():
         return
     from tests import kernel_checks as KC
     names = [n for n, _, _ in KC.ALL]
-    groups = [[n for n in names if not (n.startswith("linear") or n.startswith("conv") or n.startswith("attn")
-                                        or n.startswith("rope") or n.startswith("idx") or n.startswith("final"))],
-              [n for n in names if n.startswith("linear") or n.startswith("rope") or n.startswith("idx")],
-              [n for n in names if n.startswith("conv") or n.startswith("final")]]
-    groups += [[n] for n in names if n.startswith("attn")]
+    gemm_like = lambda n: any(n.startswith(x) for x in ("linear", "conv", "rope", "idx", "final"))  # noqa: E731
+    groups = [[n for n in names if not gemm_like(n) and not n.startswith("attn")]]
+    groups += [[n] for n in names if gemm_like(n) or n.startswith("attn")]
+    if os.environ.get("F3R_CHECK_FILTER"):
+        groups = [[n for n in g if os.environ["F3R_CHECK_FILTER"] in n] for g in groups]
+        groups = [g for g in groups if g]
     allres = {}
     for g in groups:
         try:
             p = subprocess.run([sys.executable, __file__, "--only", ",".join(g)], capture_output=True, text=True,
-                               timeout=int(os.environ.get("F3R_CHECK_TIMEOUT", "150")))
+                               timeout=int(os.environ.get("F3R_CHECK_TIMEOUT", "75")))
             out = p.stdout
             got = None
             for line in out.splitlines():
@@ -59,12 +60,13 @@ def main():
             so = e.stdout.decode() if isinstance(e.stdout, bytes) else (e.stdout or "")
             for n in g:
                 allres[n] = dict(ok=False, exc="TIMEOUT (hang)", tail=so[-500:])
+        for n in g:
+            print(("OK   " if allres[n].get("ok") else "FAIL ") + n, {k: v for k, v in allres[n].items() if k != "tb"},
+                  flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "kernel_checks.json"), "w") as f:
         json.dump(allres, f, indent=1)
     bad = [n for n, r in allres.items() if not r.get("ok")]
-    for n, r in allres.items():
-        print(("OK   " if r.get("ok") else "FAIL ") + n, {k: v for k, v in r.items() if k not in ("tb",)})
     print("FAILED:", bad)
 
 
