@@ -244,6 +244,9 @@ class Fast3R(nn.Module):
         self.max_images_per_encoder_chunk = 256
         # sequence-parallel inference (set by fast3r_b200.parallel.enable_sequence_parallel)
         self.sp_group = None
+        # None: per-rank seed offset like the reference (data parallel, fast3r.py:707-708); an int pins the offset
+        # (sequence parallel always uses 0 so that all ranks draw the single-device id stream)
+        self.image_id_rank_offset = None
         self._taps = None  # set to a dict to record per-stage tensors (parity debugging / tests)
         self._packed = None
         self._packed_sig = None
@@ -527,7 +530,7 @@ class Fast3R(nn.Module):
             profiling_info["encode_images_time"] = time.time() - t_start
         t1 = time.time()
         # image ids: same host RNG stream as the reference (all sequence-parallel ranks draw the rank-0 stream)
-        ids = self.decoder.draw_image_ids(B, N, rank_offset=0 if sp is not None else None)
+        ids = self.decoder.draw_image_ids(B, N, rank_offset=0 if sp is not None else self.image_id_rank_offset)
         if profiling:
             profiling_info["pos_emb_time"] = time.time() - t1
             torch.cuda.synchronize()

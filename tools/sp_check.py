@@ -20,6 +20,7 @@ for (n_views, batch, H, W) in [(5, 1, 64, 96), (4, 2, 48, 64), (2 * world, 1, 96
     shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
     model.load_state_dict(synth_state_dict(shapes, seed=0))
     model = model.cuda()
+    model.image_id_rank_offset = 0           # the single-device oracle stream (rank-independent)
     views = [dict(img=im.cuda()) for im in synth_images(n_views, batch, H, W)]
     torch.manual_seed(7)
     ref = model(views)                       # single-GPU forward (every rank computes it redundantly)
@@ -32,6 +33,7 @@ for (n_views, batch, H, W) in [(5, 1, 64, 96), (4, 2, 48, 64), (2 * world, 1, 96
         for k in b:
             d = (a[k].float() - b[k].float()).abs().max().item() / (b[k].float().abs().max().item() + 1e-30)
             worst = max(worst, d)
+    print(f"  rank {rank}: worst {worst:.3e}", flush=True)
     t = torch.tensor([worst], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
