@@ -18,7 +18,7 @@ namespace f3r {
 
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
-constexpr int GEMM_THREADS = 320;  // warp0 TMA, warp1 MMA(+TMEM alloc), warps 2-9 epilogue (2 per TMEM lane quarter)
+constexpr int GEMM_THREADS = 384;  // warpgroup 0: warp0 TMA, warp1 MMA(+TMEM alloc), 2 idle; warps 4-11 epilogue
 
 template <int BLOCK_N>
 struct GemmCfg {
@@ -26,14 +26,18 @@ struct GemmCfg {
   static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
   static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + 4096 /*FINAL partials*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 1024 /*barriers*/ + 8 * 4096 /*epilogue staging*/;
   static constexpr uint32_t kTmemCols = 2 * BLOCK_N;
 };
 
-// Residual operands of one 32-column chunk, fetched ahead of the TMEM load they are added to.
+// Epilogue data movement.  A thread owns one accumulator ROW (tcgen05.ld 32x32b), but row-per-thread global
+// accesses touch 32 different cache lines per instruction.  Every 32x32 fp32 chunk is therefore transposed through a
+// per-warp 4 KB shared-memory tile (16-byte chunks XOR-swizzled by row, conflict-free both ways) and all global
+// traffic (residual reads, stores) is issued in the "transposed" mapping: lane l handles 4 consecutive columns
+// (16 B fp32 / 8 B bf16) of row 4*i + l/8, i = 0..7, so one warp instruction covers 4 full 128-byte row segments.
 struct ResChunk {
-  uint4 r0[8];  // res0: 32 fp32 (8 x uint4) or 32 bf16 (first 4 x uint4)
-  uint4 r1[4];  // res1: 32 bf16
+  uint4 r0[8];  // res0 piece i: 4 fp32 (uint4) or 4 bf16 (.x,.y)
+  uint2 r1[8];  // res1 piece i: 4 bf16
 };
 
 __device__ __forceinline__ size_t out_offset(const GemmArgs& p, int m, int col0, int img, int py, int px) {
@@ -45,23 +49,23 @@ __device__ __forceinline__ size_t out_offset(const GemmArgs& p, int m, int col0,
   return static_cast<size_t>(m) * p.ldo + col0;
 }
 
-__device__ __forceinline__ void prefetch_res(const GemmArgs& p, ResChunk& rc, size_t off, bool row_ok) {
-  if (!row_ok) return;
-  if (p.res0 != nullptr) {
-    if (p.res0_f32) {
-      const uint4* r4 = reinterpret_cast<const uint4*>(static_cast<const float*>(p.res0) + off);
+// off_row / ok_row: output offset and validity of THIS lane's accumulator row; piece i needs the values of row 4*i + lane/8
+__device__ __forceinline__ void prefetch_res(const GemmArgs& p, ResChunk& rc, size_t off_row, bool ok_row, int lane) {
+  if (p.res0 == nullptr && p.res1 == nullptr) return;
+  const unsigned okmask = __ballot_sync(0xffffffffu, ok_row);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) rc.r0[i] = r4[i];
-    } else {
-      const uint4* r4 = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.res0) + off);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) rc.r0[i] = r4[i];
+  for (int i = 0; i < 8; ++i) {
+    const int rr = 4 * i + (lane >> 3);
+    const size_t off = __shfl_sync(0xffffffffu, off_row, rr) + (lane & 7) * 4;
+    if (!((okmask >> rr) & 1)) continue;
+    if (p.res0 != nullptr) {
+      if (p.res0_f32) rc.r0[i] = *reinterpret_cast<const uint4*>(static_cast<const float*>(p.res0) + off);
+      else {
+        const uint2 t = *reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(p.res0) + off);
+        rc.r0[i].x = t.x; rc.r0[i].y = t.y;
+      }
     }
-  }
-  if (p.res1 != nullptr) {
-    const uint4* r4 = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.res1) + off);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) rc.r1[i] = r4[i];
+    if (p.res1 != nullptr) rc.r1[i] = *reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(p.res1) + off);
   }
 }
 
@@ -81,10 +85,10 @@ __device__ __forceinline__ float gelu_fast(float x) {
   return 0.5f * x * (1.0f + erf_v);
 }
 
-template <int BLOCK_N>
-__device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, float (&v)[32], const ResChunk& rc, int m, int col0,
-                                               bool row_ok, size_t off, float (&fin)[4]) {
-  // ---- bias
+// Row-domain part: bias, RoPE, image-index embedding, or the FINAL 128->4 dot product.  Returns false if the chunk is
+// fully consumed here (FINAL).
+__device__ __forceinline__ bool epilogue_rows(const GemmArgs& p, float (&v)[32], int m, int col0, bool row_ok,
+                                              float (&fin)[4]) {
   if (p.bias != nullptr) {
     const float4* b4 = reinterpret_cast<const float4*>(p.bias + (p.epi == EPI_CONVT ? (col0 % p.ct_cout) : col0));
 #pragma unroll
@@ -93,9 +97,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, float (&v)[32]
       v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
     }
   }
-  if (!row_ok) return;
-
-  if (p.epi == EPI_ROPE && col0 < p.rope_cols) {
+  if (p.epi == EPI_ROPE && col0 < p.rope_cols && row_ok) {
     // RoPE2D (fast3r/croco/models/pos_embed.py:141-183): 32-wide half-head, pair (j, j+16), angle pos*base^(-j/16)
     const int t = m % p.tok_per_img;
     const int pos = ((col0 >> 5) & 1) ? (t % p.grid_w) : (t / p.grid_w);
@@ -114,7 +116,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, float (&v)[32]
       }
     }
   }
-  if (p.epi == EPI_IDXEMB) {
+  if (p.epi == EPI_IDXEMB && row_ok) {
     // + image_idx_emb[id(view of token)]  (fast3r/models/fast3r.py:785-799)
     const int id = __ldg(p.emb_ids + m / p.tok_per_img);
     const float4* e4 = reinterpret_cast<const float4*>(p.emb_table + static_cast<size_t>(id) * p.N + col0);
@@ -126,85 +128,78 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, float (&v)[32]
   }
   if (p.epi == EPI_FINAL) {
     // ReLU -> conv1x1 (BLOCK_N -> 4), accumulated across the column chunks of this row
+    if (row_ok) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const float r = fmaxf(v[i], 0.f);
+      for (int i = 0; i < 32; ++i) {
+        const float r = fmaxf(v[i], 0.f);
 #pragma unroll
-      for (int o = 0; o < 4; ++o) fin[o] = fmaf(r, __ldg(p.w4 + o * p.N + col0 + i), fin[o]);
+        for (int o = 0; o < 4; ++o) fin[o] = fmaf(r, __ldg(p.w4 + o * p.N + col0 + i), fin[o]);
+      }
     }
-    return;
+    return false;
   }
+  return true;
+}
 
-  // ---- residual adds (operands were prefetched)
-  if (p.res0 != nullptr) {
-    if (p.res0_f32) {
+// Transposed part: stage the 32x32 chunk, then residual adds / activation / stores with coalesced accesses.
+__device__ __forceinline__ void epilogue_store(const GemmArgs& p, const float (&v)[32], const ResChunk& rc, uint8_t* stage,
+                                               int lane, int m, int col0, size_t off_row, bool ok_row) {
+  // write own row: 16-byte chunk j of row r lives at r*128 + ((j ^ (r & 7)) << 4)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        v[4 * i + 0] += __uint_as_float(rc.r0[i].x); v[4 * i + 1] += __uint_as_float(rc.r0[i].y);
-        v[4 * i + 2] += __uint_as_float(rc.r0[i].z); v[4 * i + 3] += __uint_as_float(rc.r0[i].w);
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<float4*>(stage + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+        make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  __syncwarp();
+  const unsigned okmask = __ballot_sync(0xffffffffu, ok_row);
+  const int cj = lane & 7;
+  const bool to_b = p.split_col > 0 && col0 >= p.split_col;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rr = 4 * i + (lane >> 3);
+    const size_t off = __shfl_sync(0xffffffffu, off_row, rr) + cj * 4;
+    const int mrow = __shfl_sync(0xffffffffu, m, rr);
+    if (!((okmask >> rr) & 1)) continue;
+    const float4 a = *reinterpret_cast<const float4*>(stage + rr * 128 + ((cj ^ (rr & 7)) << 4));
+    float x0 = a.x, x1 = a.y, x2 = a.z, x3 = a.w;
+    if (p.res0 != nullptr) {
+      if (p.res0_f32) {
+        x0 += __uint_as_float(rc.r0[i].x); x1 += __uint_as_float(rc.r0[i].y);
+        x2 += __uint_as_float(rc.r0[i].z); x3 += __uint_as_float(rc.r0[i].w);
+      } else {
+        x0 += bf16_lo(rc.r0[i].x); x1 += bf16_hi(rc.r0[i].x); x2 += bf16_lo(rc.r0[i].y); x3 += bf16_hi(rc.r0[i].y);
       }
+    }
+    if (p.res1 != nullptr) {
+      x0 += bf16_lo(rc.r1[i].x); x1 += bf16_hi(rc.r1[i].x); x2 += bf16_lo(rc.r1[i].y); x3 += bf16_hi(rc.r1[i].y);
+    }
+    if (p.out1 != nullptr) {  // relu(v) in bf16: operand of the next 3x3 conv of a residual unit
+      uint2 o;
+      o.x = pack_bf16(fmaxf(x0, 0.f), fmaxf(x1, 0.f));
+      o.y = pack_bf16(fmaxf(x2, 0.f), fmaxf(x3, 0.f));
+      *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(p.out1) + off) = o;
+    }
+    if (p.out0 == nullptr) continue;
+    if (p.act == ACT_RELU) {
+      x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f);
+    } else if (p.act == ACT_GELU) {
+      x0 = gelu_fast(x0); x1 = gelu_fast(x1); x2 = gelu_fast(x2); x3 = gelu_fast(x3);
+    }
+    void* base = p.out0;
+    size_t o = off;
+    if (to_b) {  // q | kv column split
+      base = p.out0b;
+      o = static_cast<size_t>(mrow) * p.ldo_b + (col0 - p.split_col) + cj * 4;
+    }
+    if (p.out0_f32) {
+      *reinterpret_cast<float4*>(static_cast<float*>(base) + o) = make_float4(x0, x1, x2, x3);
     } else {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const uint32_t w[4] = {rc.r0[i].x, rc.r0[i].y, rc.r0[i].z, rc.r0[i].w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) { v[8 * i + 2 * e] += bf16_lo(w[e]); v[8 * i + 2 * e + 1] += bf16_hi(w[e]); }
-      }
+      uint2 q;
+      q.x = pack_bf16(x0, x1);
+      q.y = pack_bf16(x2, x3);
+      *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(base) + o) = q;
     }
   }
-  if (p.res1 != nullptr) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const uint32_t w[4] = {rc.r1[i].x, rc.r1[i].y, rc.r1[i].z, rc.r1[i].w};
-#pragma unroll
-      for (int e = 0; e < 4; ++e) { v[8 * i + 2 * e] += bf16_lo(w[e]); v[8 * i + 2 * e + 1] += bf16_hi(w[e]); }
-    }
-  }
-  // ---- secondary output: relu(v) in bf16 (input of the next 3x3 conv of a residual unit)
-  if (p.out1 != nullptr) {
-    uint4* o4 = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out1) + off);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      uint4 o;
-      o.x = pack_bf16(fmaxf(v[8 * i + 0], 0.f), fmaxf(v[8 * i + 1], 0.f));
-      o.y = pack_bf16(fmaxf(v[8 * i + 2], 0.f), fmaxf(v[8 * i + 3], 0.f));
-      o.z = pack_bf16(fmaxf(v[8 * i + 4], 0.f), fmaxf(v[8 * i + 5], 0.f));
-      o.w = pack_bf16(fmaxf(v[8 * i + 6], 0.f), fmaxf(v[8 * i + 7], 0.f));
-      o4[i] = o;
-    }
-  }
-  if (p.out0 == nullptr) return;
-  // ---- activation of the primary output
-  if (p.act == ACT_RELU) {
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-  } else if (p.act == ACT_GELU) {
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = gelu_fast(v[i]);
-  }
-  // ---- primary store (optionally column-split into two buffers: q | kv)
-  void* base = p.out0;
-  size_t o = off;
-  if (p.split_col > 0 && col0 >= p.split_col) {
-    base = p.out0b;
-    o = static_cast<size_t>(m) * p.ldo_b + (col0 - p.split_col);
-  }
-  if (p.out0_f32) {
-    float4* o4 = reinterpret_cast<float4*>(static_cast<float*>(base) + o);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-  } else {
-    uint4* o4 = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(base) + o);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      uint4 q;
-      q.x = pack_bf16(v[8 * i + 0], v[8 * i + 1]);
-      q.y = pack_bf16(v[8 * i + 2], v[8 * i + 3]);
-      q.z = pack_bf16(v[8 * i + 4], v[8 * i + 5]);
-      q.w = pack_bf16(v[8 * i + 6], v[8 * i + 7]);
-      o4[i] = q;
-    }
-  }
+  __syncwarp();  // staging tile is rewritten by the next chunk
 }
 
 template <int BLOCK_N>
@@ -222,7 +217,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   uint64_t* tmem_full = bars + 2 * Cfg::kStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  float* fin_smem = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + 256);  // [2][128][4]
+  uint8_t* stage_base = smem + Cfg::kStages * Cfg::kStageBytes + 1024;  // 8 x 4 KB, 1024-aligned
+  float* fin_smem = reinterpret_cast<float*>(stage_base);  // [2][128][4] (FINAL mode does not stage)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -244,6 +240,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   const int k_chunks = (p.K + BLOCK_K - 1) / BLOCK_K;
   const int k_iters = p.taps * k_chunks;
 
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");   // 384 x 168 = 128 x 72 + 256 x 216
   if (warp == 0) {
     if (lane == 0) {
       // ===================== TMA producer =====================
@@ -291,11 +289,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
+  }
   } else {
     // ===================== epilogue warps (TMEM -> regs -> global) =====================
-    // Two warps per TMEM lane quarter: warp (2+q') and (6+q') take the even / odd 32-column chunks of the tile.
+    // Two warps per TMEM lane quarter: warps (4+q) and (8+q) take the even / odd 32-column chunks of the tile.
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
     const int quarter = warp & 3;            // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;        // 0: even chunks, 1: odd chunks
+    const int half = (warp - 4) >> 2;        // 0: even chunks, 1: odd chunks
     const int r = quarter * 32 + lane;       // row inside the 128-row tile
     constexpr int kChunks = BLOCK_N / 32;
     int acc = 0; uint32_t acc_phase = 0;
@@ -308,9 +308,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       const int n_valid = min(kChunks, (p.N - nt * BLOCK_N + 31) / 32);
       ResChunk rc_cur, rc_next;
       size_t off_cur = 0, off_next = 0;
+      uint8_t* stage = stage_base + (warp - 4) * 4096;
       if (half < n_valid) {  // residual operands of the first chunk are fetched while the MMAs still run
         off_next = out_offset(p, m, nt * BLOCK_N + half * 32, img, py, px);
-        prefetch_res(p, rc_next, off_next, row_ok);
+        prefetch_res(p, rc_next, off_next, row_ok, lane);
       }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
@@ -324,13 +325,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         off_cur = off_next;
         if (c + 2 < n_valid) {
           off_next = out_offset(p, m, col0 + 64, img, py, px);
-          prefetch_res(p, rc_next, off_next, row_ok);
+          prefetch_res(p, rc_next, off_next, row_ok, lane);
         }
         tmem_ld_wait();
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
-        epilogue_chunk<BLOCK_N>(p, v, rc_cur, m, col0, row_ok, off_cur, fin);
+        if (epilogue_rows(p, v, m, col0, row_ok, fin)) epilogue_store(p, v, rc_cur, stage, lane, m, col0, off_cur, row_ok);
       }
       tc_fence_before();
       __syncwarp();
