@@ -4,6 +4,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/fast3r_b200.h"
@@ -114,6 +115,13 @@ int f3r_gemm(const f3r_gemm_desc* d, void* stream) {
     if (tiles256 >= num_sms()) block_n = 256;
   }
   a.num_n_tiles = (d->n + block_n - 1) / block_n;
+  // CTA pairs sharing the weight tile through TMA multicast (F3R_GEMM_CLUSTER=1 disables, for A/B measurements)
+  static int cluster_pref = -1;
+  if (cluster_pref < 0) {
+    const char* e = getenv("F3R_GEMM_CLUSTER");
+    cluster_pref = (e && e[0] == '1') ? 1 : 2;
+  }
+  const int cluster = (cluster_pref == 2 && a.num_m_tiles >= 2) ? 2 : 1;
   a.epi = d->epi; a.act = d->act; a.out0_f32 = d->out0_f32; a.res0_f32 = d->res0_f32;
   a.ldo = d->ldo > 0 ? d->ldo : d->n;
   a.split_col = d->split_col; a.ldo_b = d->ldo_b;
@@ -139,11 +147,11 @@ int f3r_gemm(const f3r_gemm_desc* d, void* stream) {
     const uint64_t dims[3] = {static_cast<uint64_t>(d->k), static_cast<uint64_t>(d->taps),
                               static_cast<uint64_t>(d->n)};
     const uint64_t str[2] = {static_cast<uint64_t>(d->k) * 2, static_cast<uint64_t>(d->k) * 2 * d->taps};
-    const uint32_t box[3] = {64, 1, static_cast<uint32_t>(block_n)};
+    const uint32_t box[3] = {64, 1, static_cast<uint32_t>(block_n / cluster)};
     if (make_tmap(&tb, d->wt, 3, dims, str, box)) return 1;
   }
   g_launches++;
-  return check(f3r::launch_gemm(block_n, ta, tb, a, num_sms(), static_cast<cudaStream_t>(stream)), "f3r_gemm");
+  return check(f3r::launch_gemm(block_n, cluster, ta, tb, a, num_sms(), static_cast<cudaStream_t>(stream)), "f3r_gemm");
 }
 
 int f3r_attention(const void* q, int32_t ldq, const void* kv, int32_t ldkv, void* out, int32_t ldo, float* lse,

@@ -34,8 +34,8 @@ struct GemmArgs {
   float* conf;
 };
 
-cudaError_t launch_gemm(int block_n, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, int num_sms,
-                        cudaStream_t stream);
+cudaError_t launch_gemm(int block_n, int cluster, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a,
+                        int num_sms, cudaStream_t stream);
 
 struct AttnArgs {
   int batch, heads, sq, skv;  // per-batch query / key lengths

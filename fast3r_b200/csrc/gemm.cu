@@ -202,7 +202,10 @@ __device__ __forceinline__ void epilogue_store(const GemmArgs& p, const float (&
   __syncwarp();  // staging tile is rewritten by the next chunk
 }
 
-template <int BLOCK_N>
+// kCluster = 2: CTA pairs own vertically adjacent 128-row tiles of the same BLOCK_N column block; each CTA fetches
+// half of the shared weight tile and TMA-multicasts it to both, cutting L2->SM operand traffic per FLOP by 1/3
+// (the kernel is L2-feed bound with one CTA per tile: 48 KB per 128x256x64 k-block vs ~45-55 B/clk/SM of TMA fill).
+template <int BLOCK_N, int kCluster>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
             const __grid_constant__ GemmArgs p) {
@@ -226,17 +229,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
-    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kCluster); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 8); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_ptr);
   tc_fence_before();
   __syncthreads();
+  if constexpr (kCluster > 1) cluster_sync_all();  // peer barriers are initialised before any multicast can arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  // work item = (group of kCluster vertically adjacent m-tiles, n-tile); both CTAs of a cluster walk the same items
+  const int cta_rank = kCluster > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int first_item = kCluster > 1 ? static_cast<int>(cluster_id_x()) : static_cast<int>(blockIdx.x);
+  const int item_stride = kCluster > 1 ? static_cast<int>(num_clusters_x()) : static_cast<int>(gridDim.x);
+  const int num_tiles = ((p.num_m_tiles + kCluster - 1) / kCluster) * p.num_n_tiles;
+  constexpr uint16_t kMask = (1u << kCluster) - 1;
   const int k_chunks = (p.K + BLOCK_K - 1) / BLOCK_K;
   const int k_iters = p.taps * k_chunks;
 
@@ -246,8 +255,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     if (lane == 0) {
       // ===================== TMA producer =====================
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int mt = tile / p.num_n_tiles, nt = tile % p.num_n_tiles;
+      for (int tile = first_item; tile < num_tiles; tile += item_stride) {
+        const int mt = (tile / p.num_n_tiles) * kCluster + cta_rank, nt = tile % p.num_n_tiles;
         const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, img = mt / (p.tiles_x * p.tiles_y);
         const int x0 = tx * p.bw, y0 = ty * p.bh, n0 = nt * BLOCK_N;
         for (int it = 0; it < k_iters; ++it) {
@@ -257,7 +266,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           tma_load_4d(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], kc * BLOCK_K, x0 + dx, y0 + dy, img);
-          tma_load_3d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kc * BLOCK_K, tap, n0);
+          if constexpr (kCluster == 1) {
+            tma_load_3d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kc * BLOCK_K, tap, n0);
+          } else {  // my slice of the weight tile goes to every CTA of the cluster
+            constexpr int kRows = BLOCK_N / kCluster;
+            tma_load_3d_mcast(smem_b + stage * Cfg::kBBytes + cta_rank * (kRows * BLOCK_K * 2), &tmap_b, &full_bar[stage],
+                              kc * BLOCK_K, tap, n0 + cta_rank * kRows, kMask);
+          }
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -268,7 +283,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, 0, 0);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = first_item; tile < num_tiles; tile += item_stride) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
@@ -282,7 +297,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (addr >> 4) field
             umma_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem stage once the MMAs above have read it
+          // frees the smem stage (in every CTA that multicasts into it) once the MMAs above have read it
+          if constexpr (kCluster == 1) umma_commit(&empty_bar[stage]);
+          else umma_commit_mcast(&empty_bar[stage], kMask);
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tmem_full[acc]);  // accumulator ready for the epilogue
@@ -299,11 +316,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     const int r = quarter * 32 + lane;       // row inside the 128-row tile
     constexpr int kChunks = BLOCK_N / 32;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int mt = tile / p.num_n_tiles, nt = tile % p.num_n_tiles;
+    for (int tile = first_item; tile < num_tiles; tile += item_stride) {
+      const int mt = (tile / p.num_n_tiles) * kCluster + cta_rank, nt = tile % p.num_n_tiles;
       const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, img = mt / (p.tiles_x * p.tiles_y);
       const int px = tx * p.bw + r % p.bw, py = ty * p.bh + r / p.bw;
-      const bool row_ok = (px < p.W) && (py < p.H);
+      const bool row_ok = (px < p.W) && (py < p.H) && (mt < p.num_m_tiles);
       const int m = (img * p.H + py) * p.W + px;
       const int n_valid = min(kChunks, (p.N - nt * BLOCK_N + 31) / 32);
       ResChunk rc_cur, rc_next;
@@ -358,6 +375,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (kCluster > 1) cluster_sync_all();  // no CTA leaves while its peer may still signal / multicast to it
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
@@ -365,27 +383,41 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   }
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int kCluster>
 static cudaError_t launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, int num_sms,
                                  cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BLOCK_N, kCluster>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  const int tiles = a.num_m_tiles * a.num_n_tiles;
-  const int grid = tiles < num_sms ? tiles : num_sms;
-  gemm_kernel<BLOCK_N><<<grid, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(ta, tb, a);
-  return cudaGetLastError();
+  const int items = ((a.num_m_tiles + kCluster - 1) / kCluster) * a.num_n_tiles;
+  const int max_clusters = num_sms / kCluster;
+  const int clusters = items < max_clusters ? items : max_clusters;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(clusters * kCluster);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, gemm_kernel<BLOCK_N, kCluster>, ta, tb, a);
 }
 
-cudaError_t launch_gemm(int block_n, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, int num_sms,
-                        cudaStream_t stream) {
-  if (block_n == 256) return launch_gemm_t<256>(ta, tb, a, num_sms, stream);
-  return launch_gemm_t<128>(ta, tb, a, num_sms, stream);
+cudaError_t launch_gemm(int block_n, int cluster, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a,
+                        int num_sms, cudaStream_t stream) {
+  if (block_n == 256) {
+    return cluster == 2 ? launch_gemm_t<256, 2>(ta, tb, a, num_sms, stream) : launch_gemm_t<256, 1>(ta, tb, a, num_sms, stream);
+  }
+  return cluster == 2 ? launch_gemm_t<128, 2>(ta, tb, a, num_sms, stream) : launch_gemm_t<128, 1>(ta, tb, a, num_sms, stream);
 }
 
 }  // namespace f3r
