@@ -43,9 +43,10 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
-// bf16 tensor map, 128B swizzle, zero OOB fill.  dims[0] is the contiguous dimension.
+// Tensor map with zero OOB fill.  dims[0] is the contiguous dimension.  Defaults: bf16, 128B swizzle (MMA operands).
 int make_tmap(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-              const uint32_t* box) {
+              const uint32_t* box, CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+              CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail("cuTensorMapEncodeTiled not available (no CUDA driver?)");
   cuuint64_t gd[5];
@@ -56,9 +57,8 @@ int make_tmap(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, c
   if (reinterpret_cast<uintptr_t>(ptr) & 15) return fail("tensor map base not 16-byte aligned");
   for (int i = 0; i < rank - 1; ++i)
     if (gs[i] % 16) return fail("tensor map stride %d (%llu B) not a multiple of 16", i, (unsigned long long)gs[i]);
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), gd, gs, bx, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(m, dtype, rank, const_cast<void*>(ptr), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
   return 0;
 }
@@ -107,6 +107,9 @@ int f3r_gemm(const f3r_gemm_desc* d, void* stream) {
     if (best_tiles < 0 || tiles < best_tiles) { best_tiles = tiles; best_bw = bw; }
   }
   a.bw = best_bw; a.bh = 128 / best_bw;
+  a.bw_log2 = 0;
+  while ((1 << a.bw_log2) < a.bw) ++a.bw_log2;
+  a.sbx_log2 = a.bw_log2 < 5 ? a.bw_log2 : 5;
   a.tiles_x = (d->w + a.bw - 1) / a.bw; a.tiles_y = (d->h + a.bh - 1) / a.bh;
   a.num_m_tiles = a.tiles_x * a.tiles_y * d->nb;
   int block_n = 128;
@@ -122,6 +125,10 @@ int f3r_gemm(const f3r_gemm_desc* d, void* stream) {
     cluster_pref = (e && e[0] == '1') ? 1 : 2;
   }
   const int cluster = (cluster_pref == 2 && a.num_m_tiles >= 2) ? 2 : 1;
+  static int dbg = -1, tma_pref = -1;
+  if (dbg < 0) { const char* e = getenv("F3R_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; }
+  if (tma_pref < 0) { const char* e = getenv("F3R_GEMM_TMA_EPI"); tma_pref = (e && e[0] == '0') ? 0 : 1; }
+  a.debug = dbg;
   a.epi = d->epi; a.act = d->act; a.out0_f32 = d->out0_f32; a.res0_f32 = d->res0_f32;
   a.ldo = d->ldo > 0 ? d->ldo : d->n;
   a.split_col = d->split_col; a.ldo_b = d->ldo_b;
@@ -150,8 +157,39 @@ int f3r_gemm(const f3r_gemm_desc* d, void* stream) {
     const uint32_t box[3] = {64, 1, static_cast<uint32_t>(block_n / cluster)};
     if (make_tmap(&tb, d->wt, 3, dims, str, box)) return 1;
   }
+  // TMA epilogue for the hot cases: plain (activated) stores, and the in-place fp32 residual update as a reduce-add
+  CUtensorMap to0, to0b;
+  memset(&to0, 0, sizeof(to0));
+  memset(&to0b, 0, sizeof(to0b));
+  const bool plain = (d->epi == F3R_EPI_STORE || d->epi == F3R_EPI_ROPE || d->epi == F3R_EPI_IDXEMB) && d->out0 &&
+                     !d->out1 && !d->res1;
+  if (tma_pref && plain && !d->res0) a.tma_epi = 1;
+  else if (tma_pref && plain && d->res0 == d->out0 && d->res0_f32 && d->out0_f32 && !d->split_col) a.tma_epi = 2;
+  if (a.tma_epi) {
+    const uint64_t es = d->out0_f32 ? 4 : 2;
+    const CUtensorMapDataType dt = d->out0_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    const CUtensorMapSwizzle sw = d->out0_f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    const uint32_t sbx = 1u << a.sbx_log2;
+    const uint32_t box[4] = {32, sbx, 32 / sbx, 1};
+    const uint64_t ncols0 = a.split_col ? a.split_col : d->n;
+    {
+      const uint64_t ld = static_cast<uint64_t>(a.ldo) * es;
+      const uint64_t dims[4] = {ncols0, static_cast<uint64_t>(d->w), static_cast<uint64_t>(d->h),
+                                static_cast<uint64_t>(d->nb)};
+      const uint64_t str[3] = {ld, ld * d->w, ld * d->w * d->h};
+      if (make_tmap(&to0, d->out0, 4, dims, str, box, dt, sw)) return 1;
+    }
+    if (a.split_col) {
+      const uint64_t ld = static_cast<uint64_t>(a.ldo_b) * es;
+      const uint64_t dims[4] = {static_cast<uint64_t>(d->n - a.split_col), static_cast<uint64_t>(d->w),
+                                static_cast<uint64_t>(d->h), static_cast<uint64_t>(d->nb)};
+      const uint64_t str[3] = {ld, ld * d->w, ld * d->w * d->h};
+      if (make_tmap(&to0b, d->out0b, 4, dims, str, box, dt, sw)) return 1;
+    }
+  }
   g_launches++;
-  return check(f3r::launch_gemm(block_n, cluster, ta, tb, a, num_sms(), static_cast<cudaStream_t>(stream)), "f3r_gemm");
+  return check(f3r::launch_gemm(block_n, cluster, ta, tb, to0, to0b, a, num_sms(), static_cast<cudaStream_t>(stream)),
+               "f3r_gemm");
 }
 
 int f3r_attention(const void* q, int32_t ldq, const void* kv, int32_t ldkv, void* out, int32_t ldo, float* lse,

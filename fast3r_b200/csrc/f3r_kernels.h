@@ -12,12 +12,16 @@ enum { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2 };
 struct GemmArgs {
   int M, N, K, taps;
   int W, H, NB, bw, bh, tiles_x, tiles_y;
+  int bw_log2;  // bw is a power of two
   int num_m_tiles, num_n_tiles;
   int epi, act, out0_f32, res0_f32;
   int ldo;               // row stride (elements) of out0 / out1 / res0 / res1
   int split_col, ldo_b;  // columns >= split_col go to out0b (row stride ldo_b); 0 = no split
   int tok_per_img, grid_w, rope_cols;  // EPI_ROPE / EPI_IDXEMB
   int ct_k, ct_cout;                   // EPI_CONVT
+  int tma_epi;                         // 0: generic epilogue, 1: TMA store of out0(/out0b), 2: TMA reduce-add into fp32 out0
+  int sbx_log2;                        // TMA-store box = (32 ch, sbx, 32/sbx) pixels, sbx = min(bw, 32)
+  int debug;                           // F3R_GEMM_DEBUG bitmask (1: no epilogue stores) - timing experiments only
   const float* bias;
   const void* res0;
   const void* res1;
@@ -34,8 +38,8 @@ struct GemmArgs {
   float* conf;
 };
 
-cudaError_t launch_gemm(int block_n, int cluster, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a,
-                        int num_sms, cudaStream_t stream);
+cudaError_t launch_gemm(int block_n, int cluster, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to0,
+                        const CUtensorMap& to0b, const GemmArgs& a, int num_sms, cudaStream_t stream);
 
 struct AttnArgs {
   int batch, heads, sq, skv;  // per-batch query / key lengths

@@ -202,12 +202,54 @@ __device__ __forceinline__ void epilogue_store(const GemmArgs& p, const float (&
   __syncwarp();  // staging tile is rewritten by the next chunk
 }
 
+// TMA epilogue (hot path: plain stores and the in-place fp32 residual update).  The thread that owns accumulator
+// row r writes its 32 activated values into the warp's staging tile in the tensor map's swizzled layout (conflict-free
+// 16-byte stores), then one lane hands the whole 32x32 tile to the TMA unit: a store, or for x += f(x) an fp32
+// reduce-add executed by the memory system (the residual is never read by the SM).  Out-of-range rows / columns are
+// clipped by the tensor map.
+__device__ __forceinline__ void epilogue_tma(const GemmArgs& p, float (&v)[32], uint8_t* stage, int lane,
+                                             const CUtensorMap* map, bool reduce, int c_col, int c_x, int c_y, int c_img) {
+  if (p.act == ACT_RELU) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+  } else if (p.act == ACT_GELU) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = gelu_fast(v[i]);
+  }
+  if (lane == 0) tma_store_wait_read();  // the previous tile of this warp has left the staging buffer
+  __syncwarp();
+  if (p.out0_f32) {  // 128-byte rows, SWIZZLE_128B: chunk j of row r at r*128 + ((j ^ (r & 7)) << 4)
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      *reinterpret_cast<float4*>(stage + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+          make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  } else {           // 64-byte rows, SWIZZLE_64B: chunk j of row r at r*64 + ((j ^ ((r >> 1) & 3)) << 4)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint4 q;
+      q.x = pack_bf16(v[8 * j + 0], v[8 * j + 1]);
+      q.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+      q.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
+      q.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+      *reinterpret_cast<uint4*>(stage + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = q;
+    }
+  }
+  fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
+  __syncwarp();
+  if (lane == 0) {
+    if (reduce) tma_reduce_add_4d(map, stage, c_col, c_x, c_y, c_img);
+    else tma_store_4d(map, stage, c_col, c_x, c_y, c_img);
+    tma_store_commit();
+  }
+}
+
 // kCluster = 2: CTA pairs own vertically adjacent 128-row tiles of the same BLOCK_N column block; each CTA fetches
 // half of the shared weight tile and TMA-multicasts it to both, cutting L2->SM operand traffic per FLOP by 1/3
 // (the kernel is L2-feed bound with one CTA per tile: 48 KB per 128x256x64 k-block vs ~45-55 B/clk/SM of TMA fill).
 template <int BLOCK_N, int kCluster>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+            const __grid_constant__ CUtensorMap tmap_o0, const __grid_constant__ CUtensorMap tmap_o0b,
             const __grid_constant__ GemmArgs p) {
   using Cfg = GemmCfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
@@ -326,7 +368,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       ResChunk rc_cur, rc_next;
       size_t off_cur = 0, off_next = 0;
       uint8_t* stage = stage_base + (warp - 4) * 4096;
-      if (half < n_valid) {  // residual operands of the first chunk are fetched while the MMAs still run
+      if (half < n_valid && !p.tma_epi) {  // residual operands of the first chunk are fetched while the MMAs still run
         off_next = out_offset(p, m, nt * BLOCK_N + half * 32, img, py, px);
         prefetch_res(p, rc_next, off_next, row_ok, lane);
       }
@@ -340,7 +382,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N + c * 32, raw);
         rc_cur = rc_next;
         off_cur = off_next;
-        if (c + 2 < n_valid) {
+        if (c + 2 < n_valid && !p.tma_epi) {
           off_next = out_offset(p, m, col0 + 64, img, py, px);
           prefetch_res(p, rc_next, off_next, row_ok, lane);
         }
@@ -348,7 +390,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
-        if (epilogue_rows(p, v, m, col0, row_ok, fin)) epilogue_store(p, v, rc_cur, stage, lane, m, col0, off_cur, row_ok);
+        if (epilogue_rows(p, v, m, col0, row_ok, fin) && !(p.debug & 1)) {
+          if (p.tma_epi) {
+            const bool to_b = p.split_col > 0 && col0 >= p.split_col;
+            const int r0 = quarter * 32;  // first tile row of this warp
+            epilogue_tma(p, v, stage, lane, to_b ? &tmap_o0b : &tmap_o0, p.tma_epi == 2,
+                         to_b ? col0 - p.split_col : col0, tx * p.bw + (r0 & (p.bw - 1)), ty * p.bh + (r0 >> p.bw_log2),
+                         mt < p.num_m_tiles ? img : p.NB);
+          } else {
+            epilogue_store(p, v, rc_cur, stage, lane, m, col0, off_cur, row_ok);
+          }
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -371,6 +423,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (p.tma_epi && lane == 0) tma_store_wait_all();  // bulk stores of this warp are complete before the CTA retires
   }
 
   tc_fence_before();
@@ -384,8 +437,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 }
 
 template <int BLOCK_N, int kCluster>
-static cudaError_t launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, int num_sms,
-                                 cudaStream_t stream) {
+static cudaError_t launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to0,
+                                 const CUtensorMap& to0b, const GemmArgs& a, int num_sms, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -409,15 +462,17 @@ static cudaError_t launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, c
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, gemm_kernel<BLOCK_N, kCluster>, ta, tb, a);
+  return cudaLaunchKernelEx(&cfg, gemm_kernel<BLOCK_N, kCluster>, ta, tb, to0, to0b, a);
 }
 
-cudaError_t launch_gemm(int block_n, int cluster, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a,
-                        int num_sms, cudaStream_t stream) {
+cudaError_t launch_gemm(int block_n, int cluster, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to0,
+                        const CUtensorMap& to0b, const GemmArgs& a, int num_sms, cudaStream_t stream) {
   if (block_n == 256) {
-    return cluster == 2 ? launch_gemm_t<256, 2>(ta, tb, a, num_sms, stream) : launch_gemm_t<256, 1>(ta, tb, a, num_sms, stream);
+    return cluster == 2 ? launch_gemm_t<256, 2>(ta, tb, to0, to0b, a, num_sms, stream)
+                        : launch_gemm_t<256, 1>(ta, tb, to0, to0b, a, num_sms, stream);
   }
-  return cluster == 2 ? launch_gemm_t<128, 2>(ta, tb, a, num_sms, stream) : launch_gemm_t<128, 1>(ta, tb, a, num_sms, stream);
+  return cluster == 2 ? launch_gemm_t<128, 2>(ta, tb, to0, to0b, a, num_sms, stream)
+                      : launch_gemm_t<128, 1>(ta, tb, to0, to0b, a, num_sms, stream);
 }
 
 }  // namespace f3r
