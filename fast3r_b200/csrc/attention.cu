@@ -50,6 +50,41 @@ F3R_DEVICE void fadd2(float& d0, float& d1, float a0, float a1) {
       : "+f"(d0), "+f"(d1) : "f"(a0), "f"(a1));
 }
 
+F3R_DEVICE void fsub2(float& d0, float& d1, float a0, float a1, float b0, float b1) {  // a - b
+  asm("{ .reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mov.b64 rc, {%6,%6};\n\t"
+      "fma.rn.f32x2 rd, rb, rc, ra; mov.b64 {%0,%1}, rd; }"
+      : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(-1.0f));
+}
+F3R_DEVICE void fma2v(float& d0, float& d1, float a0, float a1, float b0, float b1, float c) {  // a*b + c
+  asm("{ .reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mov.b64 rc, {%6,%6};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0,%1}, rd; }"
+      : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c));
+}
+// exp2 of a pair on the FMA / ALU pipes instead of the 16-per-clock-per-SM special-function unit: round-to-nearest
+// split x = n + f (magic-number add), degree-3 minimax polynomial of 2^f on [-0.5, 0.5] (max rel. error 7.6e-5, far
+// below the bf16 rounding of P), exponent patched in with an integer add.  x is clamped at -126 (2^-126 ~ 0).
+F3R_DEVICE void exp2_emu2(float& e0, float& e1, float x0, float x1) {
+  x0 = fmaxf(x0, -126.f); x1 = fmaxf(x1, -126.f);
+  float t0 = x0, t1 = x1;
+  fadd2(t0, t1, 12582912.f, 12582912.f);        // t = x + 1.5*2^23: low mantissa bits hold round(x)
+  float r0 = t0, r1 = t1;
+  fadd2(r0, r1, -12582912.f, -12582912.f);      // r = round(x)
+  float f0, f1;
+  fsub2(f0, f1, x0, x1, r0, r1);                // f = x - r in [-0.5, 0.5]
+  float p0, p1;
+  fma2v(p0, p1, f0, f1, 0.05520550534f, 0.05520550534f, 0.2426139712f);
+  fma2v(p0, p1, p0, p1, f0, f1, 0.6932547688f);
+  fma2v(p0, p1, p0, p1, f0, f1, 0.9999276996f);
+  e0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+  e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+}
+// bit k set: pair k of every 8 score pairs takes the FMA-pipe exp2.  Measured (profiles/r01_notes.md): in the isolated
+// softmax stream 25 % emulation is 12 % faster (2386 -> 2110 clk / iteration), but in the full kernel the decoder layer
+// at N=32 went from 2.70 ms to 2.99 ms, so it is compiled out by default (build with -DF3R_ATT_EMU_MASK=0x11 to try).
+#ifndef F3R_ATT_EMU_MASK
+#define F3R_ATT_EMU_MASK 0x0
+#endif
+
 template <int kSplit>
 __global__ void __launch_bounds__(att_threads<kSplit>(), 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
@@ -267,7 +302,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         float x0, x1, x2, x3;
         ffma2(x0, x1, __uint_as_float(s[i]), __uint_as_float(s[i + 1]), sl2, nm);
         ffma2(x2, x3, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]), sl2, nm);
-        const float e0 = ex2_approx(x0), e1 = ex2_approx(x1), e2 = ex2_approx(x2), e3 = ex2_approx(x3);
+        float e0, e1, e2, e3;
+        if ((F3R_ATT_EMU_MASK >> ((i / 2) & 7)) & 1) exp2_emu2(e0, e1, x0, x1);
+        else { e0 = ex2_approx(x0); e1 = ex2_approx(x1); }
+        if ((F3R_ATT_EMU_MASK >> ((i / 2 + 1) & 7)) & 1) exp2_emu2(e2, e3, x2, x3);
+        else { e2 = ex2_approx(x2); e3 = ex2_approx(x3); }
         fadd2(l0, l1, e0, e1);
         fadd2(l2, l3, e2, e3);
         pk[i / 2] = pack_bf16(e0, e1);
