@@ -301,7 +301,7 @@ class Fast3R(nn.Module):
         return r
 
     def _tap(self, name, t):
-        if self._taps is not None:
+        if self._taps is not None and name not in self._taps:  # first writer wins (global head before local head)
             self._taps[name] = t.detach().float().cpu().clone()
 
     # ---- packed weights
