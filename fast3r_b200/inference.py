@@ -73,7 +73,39 @@ def check_if_same_size(imgs):
     return all(shape == shapes[0] for shape in shapes)
 
 
-def _preds_to_cpu(preds):
+class _HostSink:
+    """Receives finished chunks of the model's output buffers and copies them to page-locked host memory on a side
+    stream while the model keeps computing (used by inference(); the model calls chunk_done after each head chunk)."""
+    _streams = {}
+
+    def __init__(self, device):
+        self.host = {}  # device storage ptr -> pinned uint8 host buffer of the same size
+        key = (device.type, device.index)
+        if key not in _HostSink._streams:
+            _HostSink._streams[key] = torch.cuda.Stream(device=device)
+        self.stream = _HostSink._streams[key]
+
+    def chunk_done(self, tensors, start, count):
+        ev = torch.cuda.Event()
+        ev.record()
+        self.stream.wait_event(ev)
+        with torch.cuda.stream(self.stream):
+            for t in tensors:
+                st = t.untyped_storage()
+                k = st.data_ptr()
+                if k not in self.host:
+                    self.host[k] = torch.empty(st.nbytes(), dtype=torch.uint8, pin_memory=True)
+                row = t[0].numel() * t.element_size()
+                lo, hi = t.storage_offset() * t.element_size() + start * row, t.storage_offset() * t.element_size() + (start + count) * row
+                dev_bytes = torch.empty(0, dtype=torch.uint8, device=t.device).set_(st)
+                self.host[k][lo:hi].copy_(dev_bytes[lo:hi], non_blocking=True)
+
+    def finish(self):
+        self.stream.synchronize()
+        return self.host
+
+
+def _preds_to_cpu(preds, prefilled=None):
     """D2H of the predictions (§8 f1).  The per-view tensors are slices of a few large device buffers; each
     distinct buffer is copied ONCE, asynchronously, into page-locked host memory (torch's caching host allocator
     recycles the blocks, results own their memory) and the per-view CPU tensors are rebuilt as views of it.
@@ -86,8 +118,10 @@ def _preds_to_cpu(preds):
                 groups.setdefault(st.data_ptr(), (st, v.device))
     if not groups:
         return to_cpu(preds)
-    host = {}
+    host = dict(prefilled or {})
     for key, (st, dev) in groups.items():
+        if key in host:
+            continue  # already streamed to the host chunk by chunk during the forward
         dev_bytes = torch.empty(0, dtype=torch.uint8, device=dev).set_(st)
         h = torch.empty(dev_bytes.numel(), dtype=torch.uint8, pin_memory=True)
         h.copy_(dev_bytes, non_blocking=True)
@@ -139,11 +173,18 @@ def inference(multiple_views_in_one_sample, model, device, dtype, verbose=True, 
     multiple_shapes = not check_if_same_size(multiple_views_in_one_sample)
     global _KEEP_HOST_REFS
     _KEEP_HOST_REFS = True
+    dev = torch.device(device)
+    sink = _HostSink(dev) if (dev.type == "cuda" and hasattr(model, "_host_sink")) else None
     try:
+        if sink is not None:
+            model._host_sink = sink
         res = loss_of_one_batch(collate_with_cat([tuple(multiple_views_in_one_sample)]), model, None, device, dtype,
                                 profiling=profiling)
     finally:
         _KEEP_HOST_REFS = False
+        if sink is not None:
+            model._host_sink = None
+    prefilled = sink.finish() if sink is not None else None
     profiling_info = None
     if profiling and "profiling_info" in res:
         profiling_info = res.pop("profiling_info")
@@ -153,7 +194,7 @@ def inference(multiple_views_in_one_sample, model, device, dtype, verbose=True, 
     for view in res["views"]:
         host = view.pop("_host_copy", {})
         views_cpu.append({k: (host[k] if k in host else to_cpu(v)) for k, v in view.items()})
-    res = dict(views=views_cpu, preds=_preds_to_cpu(res["preds"]), loss=to_cpu(res["loss"]))
+    res = dict(views=views_cpu, preds=_preds_to_cpu(res["preds"], prefilled), loss=to_cpu(res["loss"]))
     result.append(res)
     result = collate_with_cat(result, lists=multiple_shapes)
     if profiling and profiling_info is not None:

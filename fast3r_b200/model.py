@@ -248,6 +248,7 @@ class Fast3R(nn.Module):
         # (sequence parallel always uses 0 so that all ranks draw the single-device id stream)
         self.image_id_rank_offset = None
         self._taps = None  # set to a dict to record per-stage tensors (parity debugging / tests)
+        self._host_sink = None  # set by inference(): streams finished head chunks to pinned host memory
         self._packed = None
         self._packed_sig = None
         self.set_freeze(freeze)
@@ -568,6 +569,8 @@ class Fast3R(nn.Module):
             hk = [t[s * P:(s + c) * P] for t in hooked]
             for suffix, hw in heads:
                 self._dpt(hk, c, gh, gw, H, W, hw, outs["pts" + suffix][s:s + c], outs["conf" + suffix][s:s + c])
+            if self._host_sink is not None:  # D2H of this chunk overlaps the heads of the next one
+                self._host_sink.chunk_done(list(outs.values()), s, c)
         final_results = [{} for _ in range(N)]
         for i in range(lo, hi):
             j = i - lo
