@@ -137,47 +137,50 @@ cudaError_t launch_im2col3x3s2(const void* in, void* out, int n, int H, int W, i
 // 374): src = dst * (in-1)/(full-1), full = 2*in; only the top-left Ho x Wo window of the full output is produced
 // (Ho < full implements the crop of refinenet4's output, fast3r/dust3r/heads/dpt_head.py:69-71).
 __global__ void __launch_bounds__(256) upsample2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out,
-                                                         int n, int H, int W, int C8, int Ho, int Wo, float sy,
+                                                         int H, int W, int C8, int c8_shift, int Ho, int Wo, float sy,
                                                          float sx) {
-  const size_t total = static_cast<size_t>(n) * Ho * Wo * C8;
-  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int c = idx % C8;
-    const size_t pix = idx / C8;
-    const int ox = pix % Wo, oy = (pix / Wo) % Ho;
-    const size_t im = pix / (static_cast<size_t>(Wo) * Ho);
-    const float fy = sy * oy, fx = sx * ox;
-    const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
-    const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
-    const float ly = fy - y0, lx = fx - x0;
-    const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
-    const uint4* base = in + im * H * W * C8 + c;
-    const uint4 a = __ldg(base + (static_cast<size_t>(y0) * W + x0) * C8);
-    const uint4 b = __ldg(base + (static_cast<size_t>(y0) * W + x1) * C8);
-    const uint4 d = __ldg(base + (static_cast<size_t>(y1) * W + x0) * C8);
-    const uint4 e = __ldg(base + (static_cast<size_t>(y1) * W + x1) * C8);
-    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
-    const uint32_t dw[4] = {d.x, d.y, d.z, d.w}, ew[4] = {e.x, e.y, e.z, e.w};
-    uint32_t ow[4];
+  // blockIdx.z = image, blockIdx.y = output row, x covers (ox, 8-channel group) of that row: the row interpolation
+  // weights are per block, the only per-thread index math is one shift/mask (C8 is a power of two: 16 or 32 here)
+  const int oy = blockIdx.y;
+  const size_t im = blockIdx.z;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= Wo * C8) return;
+  const int c = t & (C8 - 1), ox = t >> c8_shift;
+  const float fy = sy * oy, fx = sx * ox;
+  const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
+  const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+  const float ly = fy - y0, lx = fx - x0;
+  const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+  const uint4* base = in + im * H * W * C8 + c;
+  const uint4 a = __ldg(base + (static_cast<size_t>(y0) * W + x0) * C8);
+  const uint4 b = __ldg(base + (static_cast<size_t>(y0) * W + x1) * C8);
+  const uint4 d = __ldg(base + (static_cast<size_t>(y1) * W + x0) * C8);
+  const uint4 e = __ldg(base + (static_cast<size_t>(y1) * W + x1) * C8);
+  const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+  const uint32_t dw[4] = {d.x, d.y, d.z, d.w}, ew[4] = {e.x, e.y, e.z, e.w};
+  uint32_t ow[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float lo = w00 * bf16_lo(aw[i]) + w01 * bf16_lo(bw[i]) + w10 * bf16_lo(dw[i]) + w11 * bf16_lo(ew[i]);
-      const float hi = w00 * bf16_hi(aw[i]) + w01 * bf16_hi(bw[i]) + w10 * bf16_hi(dw[i]) + w11 * bf16_hi(ew[i]);
-      ow[i] = pack_bf16(lo, hi);
-    }
-    out[idx] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+  for (int i = 0; i < 4; ++i) {
+    const float lo = w00 * bf16_lo(aw[i]) + w01 * bf16_lo(bw[i]) + w10 * bf16_lo(dw[i]) + w11 * bf16_lo(ew[i]);
+    const float hi = w00 * bf16_hi(aw[i]) + w01 * bf16_hi(bw[i]) + w10 * bf16_hi(dw[i]) + w11 * bf16_hi(ew[i]);
+    ow[i] = pack_bf16(lo, hi);
   }
+  out[((im * Ho + oy) * Wo + ox) * C8 + c] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
 }
 cudaError_t launch_upsample2x(const void* in, void* out, int n, int H, int W, int C, int Ho, int Wo, int Hfull,
                               int Wfull, cudaStream_t stream) {
   if (C % 8 || Hfull < 2 || Wfull < 2) return cudaErrorInvalidValue;
-  const size_t total = static_cast<size_t>(n) * Ho * Wo * (C / 8);
-  if (total == 0) return cudaSuccess;
+  const int C8 = C / 8;
+  int shift = 0;
+  while ((1 << shift) < C8) ++shift;
+  if ((1 << shift) != C8) return cudaErrorInvalidValue;  // channel count / 8 must be a power of two
+  if (n <= 0 || Ho <= 0 || Wo <= 0) return cudaSuccess;
+  if (n > 65535 || Ho > 65535) return cudaErrorInvalidValue;
   const float sy = static_cast<float>(H - 1) / static_cast<float>(Hfull - 1);
   const float sx = static_cast<float>(W - 1) / static_cast<float>(Wfull - 1);
-  const int grid = static_cast<int>(total / 256 + 1 < 148 * 16 ? total / 256 + 1 : 148 * 16);
-  upsample2x_kernel<<<grid, 256, 0, stream>>>(static_cast<const uint4*>(in), static_cast<uint4*>(out), n, H, W,
-                                              C / 8, Ho, Wo, sy, sx);
+  dim3 grid((Wo * C8 + 255) / 256, Ho, n);
+  upsample2x_kernel<<<grid, 256, 0, stream>>>(static_cast<const uint4*>(in), static_cast<uint4*>(out), H, W, C8, shift,
+                                              Ho, Wo, sy, sx);
   return cudaGetLastError();
 }
 

@@ -73,13 +73,15 @@ __device__ __forceinline__ void prefetch_res(const GemmArgs& p, ResChunk& rc, si
 // (|abs err| <= 1.5e-7, far below the bf16 rounding of the stored activation); 2 MUFU + ~12 FMA-class ops.
 __device__ __forceinline__ float gelu_fast(float x) {
   const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
   poly = fmaf(poly, t, 0.254829592f);
   poly *= t;
-  const float e = exp2f(-1.4426950408889634f * z * z);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * z * z));
   const float erf_abs = fmaf(-poly, e, 1.0f);
   const float erf_v = copysignf(erf_abs, x);
   return 0.5f * x * (1.0f + erf_v);
