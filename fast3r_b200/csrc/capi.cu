@@ -92,7 +92,7 @@ int f3r_gemm(const f3r_gemm_desc* d, void* stream) {
     return fail("f3r_gemm: bad CONVT geometry");
   if (d->epi == F3R_EPI_ROPE && (!d->rope_cos || !d->rope_sin || d->tok_per_img <= 0 || d->grid_w <= 0))
     return fail("f3r_gemm: bad ROPE arguments");
-  if (d->epi == F3R_EPI_IDXEMB && (!d->emb_table || !d->emb_ids || d->tok_per_img <= 0))
+  if (d->epi == F3R_EPI_IDXEMB && (!d->emb_table || !d->emb_ids || d->tok_per_img < 0))
     return fail("f3r_gemm: bad IDXEMB arguments");
 
   f3r::GemmArgs a;

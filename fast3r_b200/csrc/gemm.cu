@@ -120,7 +120,7 @@ __device__ __forceinline__ bool epilogue_rows(const GemmArgs& p, float (&v)[32],
   }
   if (p.epi == EPI_IDXEMB && row_ok) {
     // + image_idx_emb[id(view of token)]  (fast3r/models/fast3r.py:785-799)
-    const int id = __ldg(p.emb_ids + m / p.tok_per_img);
+    const int id = __ldg(p.emb_ids + (p.tok_per_img > 0 ? m / p.tok_per_img : m));  // per-image or per-row ids
     const float4* e4 = reinterpret_cast<const float4*>(p.emb_table + static_cast<size_t>(id) * p.N + col0);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {

@@ -389,13 +389,17 @@ class Fast3R(nn.Module):
         return feats, P, gh, gw
 
     # ---- fusion decoder (fast3r/models/fast3r.py:768-808)
-    def _decode(self, feats_bnp: torch.Tensor, ids: torch.Tensor, B: int, n_local: int, P: int, P_, kv_exchange=None):
+    def _decode(self, feats_bnp: torch.Tensor, ids: torch.Tensor, B: int, n_local: int, P: int, P_, kv_exchange=None,
+                per_token_ids: bool = False):
+        """feats_bnp: (B*seq, D) tokens in (b, view, patch) order.  ids: (B, n_local) table rows per view (P tokens
+        each), or with per_token_ids=True a flat (B*seq,) tensor with one table row per token (mixed resolutions;
+        then n_local * P must still equal the per-sample sequence length)."""
         dec = self.decoder
         D = dec.embed_dim
         M = feats_bnp.shape[0]
         dev = feats_bnp.device
         x = torch.empty(M, D, dtype=F32, device=dev)
-        ops.linear(feats_bnp, P_["de_w"], P_["de_b"], out0=x, epi=L.EPI_IDXEMB, tok_per_img=P,
+        ops.linear(feats_bnp, P_["de_w"], P_["de_b"], out0=x, epi=L.EPI_IDXEMB, tok_per_img=0 if per_token_ids else P,
                    emb_table=P_["table"], emb_ids=ids.to(device=dev, dtype=torch.int32).contiguous())
         hd = D // dec.num_heads
         if (not self.training) and dec.attn_bias_for_inference_enabled:
@@ -492,6 +496,109 @@ class Fast3R(nn.Module):
         ops.gemm(up, hw.h2[0], w=W, h=H, nb=nv, taps=9, bias=hw.h2[1], epi=L.EPI_FINAL, w4=hw.w4, b4=hw.b4,
                  pts=pts, conf=conf)
 
+    # ---- views of different resolutions (fast3r/models/fast3r.py:276-294, 364-376, 407-428)
+    def _forward_mixed(self, views, profiling=False):
+        """The reference encodes and decodes heads view by view when resolutions differ; here views are grouped by
+        shape (same arithmetic per view, batched per group), the fusion decoder runs once over the concatenation of
+        all tokens in view order with one image-index-embedding row per token."""
+        if self.sp_group is not None:
+            raise NotImplementedError("fast3r_b200: sequence parallel needs views of one resolution")
+        profiling_info = {} if profiling else None
+        t_start = time.time()
+        device = views[0]["img"].device
+        P_ = self._pack(device)
+        N = len(views)
+        B = views[0]["img"].shape[0]
+        ps = self.encoder.patch_size
+        groups: Dict[tuple, List[int]] = {}
+        for i, v in enumerate(views):
+            b, _, H, W = v["img"].shape
+            if b != B:
+                raise ValueError("all views must have the same batch size")
+            if H % ps or W % ps:
+                raise AssertionError(f"Input image size ({H}x{W}) is not a multiple of patch size ({ps}).")
+            groups.setdefault((H, W), []).append(i)
+        D = self.encoder.embed_dim
+        tok = [0] * N            # tokens per view
+        genc = {}
+        for (H, W), idxs in groups.items():
+            imgs = torch.cat([views[i]["img"] for i in idxs], dim=0).to(dtype=F32).contiguous()
+            feats, P, gh, gw = self._encode(imgs, P_)  # ((n_g*B)*P, D) in (n, b, p) order
+            genc[(H, W)] = (feats, P, gh, gw)
+            for i in idxs:
+                tok[i] = P
+        if profiling:
+            torch.cuda.synchronize()
+            profiling_info["encode_images_time"] = time.time() - t_start
+        t1 = time.time()
+        ids = self.decoder.draw_image_ids(B, N, rank_offset=self.image_id_rank_offset)
+        off = [0]
+        for i in range(N):
+            off.append(off[-1] + tok[i])
+        S = off[-1]
+        if profiling:
+            profiling_info["pos_emb_time"] = time.time() - t1
+            torch.cuda.synchronize()
+        t2 = time.time()
+        # scatter the per-group encoder outputs into (b, view, patch) order
+        feats_bnp = torch.empty(B * S, D, dtype=BF16, device=device)
+        tok_ids = torch.empty(B, S, dtype=torch.int32)
+        for (H, W), idxs in groups.items():
+            feats, P, _, _ = genc[(H, W)]
+            fv = feats.view(len(idxs), B, P, D)
+            for k, i in enumerate(idxs):
+                for b in range(B):
+                    feats_bnp[b * S + off[i]: b * S + off[i] + P] = fv[k, b]
+                    tok_ids[b, off[i]: off[i] + P] = int(ids[b, i])
+        h12, h18, h24 = self._decode(feats_bnp, tok_ids.reshape(-1), B, 1, S, P_, per_token_ids=True)
+        if profiling:
+            torch.cuda.synchronize()
+            profiling_info["decoder_time"] = time.time() - t2
+        t3 = time.time()
+        Dd = self.decoder.embed_dim
+        heads = [("", P_["head"])] + ([("_local", P_["head_local"])] if P_["head_local"] is not None else [])
+        final_results = [{} for _ in range(N)]
+        t4 = time.time()
+        for (H, W), idxs in groups.items():
+            feats, P, gh, gw = genc[(H, W)]
+            ng = len(idxs)
+
+            def regroup(t):  # (b, view, patch) -> '(n b) p' for this group's views
+                o = torch.empty(ng * B * P, Dd, dtype=BF16, device=device)
+                ov = o.view(ng, B, P, Dd)
+                for k, i in enumerate(idxs):
+                    for b in range(B):
+                        ov[k, b] = t[b * S + off[i]: b * S + off[i] + P]
+                return o
+
+            hooked = [feats, regroup(h12), regroup(h18), regroup(h24)]
+            nvt = ng * B
+            outs = {}
+            for suffix, _hw in heads:
+                outs["pts" + suffix] = torch.empty(nvt, H, W, 3, dtype=F32, device=device)
+                outs["conf" + suffix] = torch.empty(nvt, H, W, dtype=F32, device=device)
+            step = max(1, int(self.max_parallel_views_for_head))
+            for s in range(0, nvt, step):
+                c = min(step, nvt - s)
+                hk = [t[s * P:(s + c) * P] for t in hooked]
+                for suffix, hw in heads:
+                    self._dpt(hk, c, gh, gw, H, W, hw, outs["pts" + suffix][s:s + c], outs["conf" + suffix][s:s + c])
+            for k, i in enumerate(idxs):
+                r = final_results[i]
+                r["pts3d_in_other_view"] = outs["pts"][k * B:(k + 1) * B]
+                r["conf"] = outs["conf"][k * B:(k + 1) * B]
+                if "pts_local" in outs:
+                    r["pts3d_local"] = outs["pts_local"][k * B:(k + 1) * B]
+                    r["conf_local"] = outs["conf_local"][k * B:(k + 1) * B]
+        if profiling:
+            torch.cuda.synchronize()
+            t_end = time.time()
+            profiling_info["head_prepare_input_time"] = t4 - t3
+            profiling_info["head_forward_time"] = t_end - t4
+            profiling_info["total_time"] = t_end - t_start
+            return final_results, profiling_info
+        return final_results
+
     # ---- forward (fast3r/models/fast3r.py:302-497)
     @torch.no_grad()
     def forward(self, views, profiling=False):
@@ -501,8 +608,7 @@ class Fast3R(nn.Module):
         t_start = time.time()
         same_shape = all(v["img"].shape == views[0]["img"].shape for v in views)
         if not same_shape:
-            raise NotImplementedError("fast3r_b200: all views of one forward must share one resolution "
-                                      "(the reference's per-view fallback path, fast3r.py:281-294, is not built)")
+            return self._forward_mixed(views, profiling)
         device = views[0]["img"].device
         P_ = self._pack(device)
         N = len(views)

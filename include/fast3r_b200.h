@@ -50,7 +50,8 @@ typedef struct f3r_gemm_desc {
   int32_t ldo;         /* row stride (elements) of out0 / out1 / res0 / res1                                   */
   int32_t split_col, ldo_b; /* columns >= split_col of out0 go to out0b (row stride ldo_b); 0 disables         */
   int32_t tok_per_img, grid_w, rope_cols; /* ROPE: tokens per image, patch-grid width, #leading columns rotated;
-                                             IDXEMB: tok_per_img tokens share emb_ids[m / tok_per_img]         */
+                                             IDXEMB: tok_per_img tokens share emb_ids[m / tok_per_img];
+                                             tok_per_img == 0: one id per row, emb_ids[m]                     */
   int32_t ct_k, ct_cout;                  /* CONVT: kernel==stride k, out channels; n == k*k*ct_cout           */
   const float* bias;   /* [n] (CONVT: [ct_cout]) or NULL                                                       */
   const void* res0;    /* fp32 or bf16 [M, ldo] or NULL (may alias out0: in-place residual stream update)      */
@@ -61,7 +62,7 @@ typedef struct f3r_gemm_desc {
   const float* rope_cos; /* [max_pos, 16] cos(pos * base^(-j/16))                                              */
   const float* rope_sin;
   const float* emb_table; /* fp32 [1000, n]                                                                    */
-  const int32_t* emb_ids; /* int32 [M / tok_per_img]                                                           */
+  const int32_t* emb_ids; /* int32 [M / tok_per_img] (or [M] when tok_per_img == 0)                            */
   const float* w4;     /* FINAL: fp32 [4, n] 1x1 conv weight, b4 fp32 [4]                                      */
   const float* b4;
   float* pts;          /* FINAL: fp32 [M, 3]                                                                   */

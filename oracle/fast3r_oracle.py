@@ -182,12 +182,16 @@ def decoder(feats: Tensor, image_ids: Tensor, p: Dict[str, Tensor], depth: int, 
     feats: (B, N, P, D) encoder outputs; image_ids: (B, N) embedding-table rows per view.
     Returns the 1+depth layer outputs (B, N*P, D); last one through dec_norm (eps 1e-6);
     decoder blocks use LN eps 1e-5 (:683), no RoPE, eval scale 0.16019 (blocks.py:151-154)."""
-    B, N, P, D = feats.shape
-    x = feats.reshape(B, N * P, D)
+    if feats.dim() == 4:
+        B, N, P, D = feats.shape
+        x = feats.reshape(B, N * P, D)
+        tok_rows = image_ids[:, :, None].expand(B, N, P).reshape(B, N * P)
+    else:  # (B, S, D) with one table row per token (views of different resolutions)
+        x, tok_rows = feats, image_ids
     outs = [x]
     x = F.linear(x, p["decoder.decoder_embed.weight"], p["decoder.decoder_embed.bias"])
     table = image_idx_table(x.shape[-1])
-    x = x + table[image_ids][:, :, None, :].expand(B, N, P, -1).reshape(B, N * P, -1)
+    x = x + table[tok_rows]
     if taps is not None:
         taps["dec_embed"] = x.clone()
     hd = x.shape[-1] // num_heads
@@ -272,6 +276,8 @@ def forward(state_dict: Dict[str, Tensor], enc_args: dict, dec_args: dict, head_
     global torch RNG exactly like the reference does (seed before calling)."""
     p = {k: v.detach().float() for k, v in state_dict.items()}
     N = len(imgs)
+    if any(im.shape != imgs[0].shape for im in imgs):
+        return _forward_mixed(p, enc_args, dec_args, head_args, imgs, image_ids, training, rank)
     B, _, H, W = imgs[0].shape
     x = torch.cat(list(imgs), dim=0).float()  # (N*B,3,H,W), view-major (fast3r.py:258)
     feats, _pos = encoder(x, p, enc_args["depth"], enc_args["num_heads"], taps)
@@ -303,6 +309,37 @@ def forward(state_dict: Dict[str, Tensor], enc_args: dict, dec_args: dict, head_
         for i in range(N):
             preds[i]["pts3d_local"] = res_l["pts3d"][i * B:(i + 1) * B]
             preds[i]["conf_local"] = res_l["conf"][i * B:(i + 1) * B]
+    return preds
+
+
+def _forward_mixed(p, enc_args, dec_args, head_args, imgs, image_ids, training, rank):
+    """Different resolutions per view: per-view encoder and heads, one decoder pass over all tokens in view order
+    (fast3r/models/fast3r.py:276-294, 339-348, 364-376, 407-428)."""
+    N = len(imgs)
+    B = imgs[0].shape[0]
+    feats = [encoder(im.float(), p, enc_args["depth"], enc_args["num_heads"])[0] for im in imgs]  # (B, P_i, D)
+    if image_ids is None:
+        image_ids = draw_image_ids(B, N, rank) if dec_args.get("random_image_idx_embedding", True) \
+            else torch.arange(N)[None].expand(B, N)
+    x = torch.cat(feats, dim=1)
+    tok_rows = torch.cat([image_ids[:, i:i + 1].expand(B, f.shape[1]) for i, f in enumerate(feats)], dim=1)
+    outs = decoder(x, tok_rows, p, dec_args["depth"], dec_args["num_heads"], training,
+                   dec_args.get("attn_bias_for_inference_enabled", True))
+    d = dec_args["depth"]
+    hooks = [0, d * 2 // 4, d * 3 // 4, d]
+    preds = []
+    off = 0
+    for i, im in enumerate(imgs):
+        P_i = feats[i].shape[1]
+        hooked = [outs[h][:, off:off + P_i] for h in hooks]
+        off += P_i
+        H, W = im.shape[-2:]
+        r = postprocess(dpt_head(hooked, H, W, p, "downstream_head.", head_args.get("patch_size", 16)))
+        pr = dict(pts3d_in_other_view=r["pts3d"], conf=r["conf"])
+        if head_args.get("with_local_head", False):
+            rl = postprocess(dpt_head(hooked, H, W, p, "downstream_head_local.", head_args.get("patch_size", 16)))
+            pr.update(pts3d_local=rl["pts3d"], conf_local=rl["conf"])
+        preds.append(pr)
     return preds
 
 

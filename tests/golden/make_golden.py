@@ -24,8 +24,10 @@ def half(t):
     return t.detach().clone()
 
 
-def run_tiny(B, N, H, W, tag):
+def run_tiny(B, N, H, W, tag, dec_over=None, head_over=None):
     enc, dec, head = tiny_args()
+    dec.update(dec_over or {})
+    head.update(head_over or {})
     torch.manual_seed(0)
     model = Fast3R(dict(enc), dict(dec), dict(head)).eval()
     shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
@@ -66,11 +68,12 @@ def run_tiny(B, N, H, W, tag):
     torch.manual_seed(7)
     with torch.no_grad():
         preds = model(views)
-    keep = None if B == 1 else ()
+    keep = None if (B == 1 and not dec_over and not head_over) else ()
     snap = {k: v for k, v in taps.items() if keep is None or k in keep}  # snapshot (later runs re-fire the hooks)
     out = dict(shapes=shapes, taps=snap, image_ids=ids, B=B, N=N, H=H, W=W, weight_seed=0, rng_seed=7,
+               dec_over=dec_over or {}, head_over=head_over or {},
                preds=[{k: half(v) for k, v in p.items()} for p in preds])
-    if B == 1:
+    if B == 1 and not dec_over and not head_over:
         # the public API on the same inputs (inference(): collate, dtype="32", to_cpu)
         views1 = [dict(img=imgs[i], true_shape=np.int32([[H, W]]), idx=i, instance=str(i),
                        dataset="synthetic", label=f"v{i}") for i in range(N)]
@@ -95,6 +98,27 @@ def run_tiny(B, N, H, W, tag):
     sz = os.path.getsize(os.path.join(HERE, f"{tag}.pt"))
     print(tag, "saved", sz / 1e6, "MB; pts abs mean", preds[0]["pts3d_in_other_view"].abs().mean().item(),
           "conf mean", preds[0]["conf"].mean().item())
+
+
+def run_tiny_mixed(tag="tiny_mixed_res"):
+    """Views of different resolutions in one forward (reference per-view path, fast3r/models/fast3r.py:276-294, 407-428)."""
+    enc, dec, head = tiny_args()
+    torch.manual_seed(0)
+    model = Fast3R(dict(enc), dict(dec), dict(head)).eval()
+    shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    model.load_state_dict(synth_state_dict(shapes, seed=0))
+    sizes = [(64, 96), (48, 64), (64, 96), (32, 48)]
+    B = 1
+    imgs = [synth_images(1, B, h, w, seed0=1234 + i)[0] for i, (h, w) in enumerate(sizes)]
+    views = [dict(img=imgs[i], true_shape=torch.tensor([[h, w]] * B, dtype=torch.int32), idx=i, instance=str(i),
+                  dataset="synthetic", label=f"v{i}") for i, (h, w) in enumerate(sizes)]
+    torch.manual_seed(7)
+    with torch.no_grad():
+        preds = model(views)
+    out = dict(shapes=shapes, sizes=sizes, B=B, weight_seed=0, rng_seed=7,
+               preds=[{k: half(v) for k, v in p.items()} for p in preds])
+    torch.save(out, os.path.join(HERE, f"{tag}.pt"))
+    print(tag, "saved", os.path.getsize(os.path.join(HERE, f"{tag}.pt")) / 1e6, "MB")
 
 
 def run_blocks():
@@ -131,4 +155,10 @@ def run_blocks():
 if __name__ == "__main__":
     run_tiny(1, 3, 64, 96, "tiny_b1_n3")
     run_tiny(2, 2, 48, 64, "tiny_b2_n2")
+    # configuration quirks the replacement must honour
+    run_tiny(1, 3, 64, 96, "tiny_noattnbias", dec_over=dict(attn_bias_for_inference_enabled=False))
+    run_tiny(1, 3, 64, 96, "tiny_fixedidx", dec_over=dict(random_image_idx_embedding=False))
+    run_tiny(1, 2, 32, 48, "tiny_nolocal_n2", head_over=dict(with_local_head=False))
+    run_tiny(1, 1, 48, 48, "tiny_single_view")
+    run_tiny_mixed()
     run_blocks()

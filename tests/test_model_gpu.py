@@ -19,14 +19,18 @@ from tests.golden.synth import synth_state_dict, synth_images  # noqa: E402
 def _build(tag, golden_dir):
     from fast3r_b200 import Fast3R, tiny_args
     g = torch.load(os.path.join(golden_dir, f"{tag}.pt"))
-    model = Fast3R(*tiny_args()).eval()
+    enc, dec, head = tiny_args()
+    dec.update(g.get("dec_over", {}))
+    head.update(g.get("head_over", {}))
+    model = Fast3R(enc, dec, head).eval()
     model.load_state_dict(synth_state_dict(g["shapes"], seed=g["weight_seed"]))
     model = model.cuda()
     imgs = synth_images(g["N"], g["B"], g["H"], g["W"])
     return g, model, imgs
 
 
-@pytest.mark.parametrize("tag", ["tiny_b1_n3", "tiny_b2_n2"])
+@pytest.mark.parametrize("tag", ["tiny_b1_n3", "tiny_b2_n2", "tiny_noattnbias", "tiny_fixedidx", "tiny_nolocal_n2",
+                                 "tiny_single_view"])
 def test_tiny_vs_reference_golden(golden_dir, tag):
     g, model, imgs = _build(tag, golden_dir)
     views = [dict(img=im.cuda(), true_shape=torch.tensor([[g["H"], g["W"]]] * g["B"]), idx=i, instance=str(i))
@@ -53,6 +57,28 @@ def test_tiny_vs_reference_golden(golden_dir, tag):
     for k in g["preds"][0]:
         assert preds[0][k].shape == g["preds"][0][k].shape and preds[0][k].dtype == torch.float32
         assert report[k] <= max(gap[k], 5e-3), (k, report)
+
+
+def test_mixed_resolution_vs_reference_golden(golden_dir):
+    """Views of different resolutions in one forward (reference per-view path) against reference outputs."""
+    from fast3r_b200 import Fast3R, tiny_args
+    g = torch.load(os.path.join(golden_dir, "tiny_mixed_res.pt"))
+    model = Fast3R(*tiny_args()).eval()
+    model.load_state_dict(synth_state_dict(g["shapes"], seed=g["weight_seed"]))
+    model = model.cuda()
+    imgs = [synth_images(1, g["B"], h, w, seed0=1234 + i)[0] for i, (h, w) in enumerate(g["sizes"])]
+    torch.manual_seed(g["rng_seed"])
+    preds = model([dict(img=im.cuda()) for im in imgs])
+    rep = {}
+    for k in g["preds"][0]:
+        a = torch.cat([p[k].float().cpu().flatten() for p in preds])
+        b = torch.cat([p[k].float().flatten() for p in g["preds"]])
+        rep[k] = rel_l2(a, b)
+    print("mixed", rep)
+    for i, q in enumerate(g["preds"]):
+        for k in q:
+            assert preds[i][k].shape == q[k].shape
+    assert all(v < 2e-2 for v in rep.values()), rep
 
 
 def test_inference_api_vs_golden(golden_dir):

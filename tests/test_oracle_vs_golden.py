@@ -12,10 +12,15 @@ from tests.golden.synth import synth_state_dict, synth_images
 TOL = 2e-5  # fp32 CPU, different summation order (SDPA-flash vs naive, conv algorithms)
 
 
-@pytest.mark.parametrize("tag", ["tiny_b1_n3", "tiny_b2_n2"])
+ALL_TAGS = ["tiny_b1_n3", "tiny_b2_n2", "tiny_noattnbias", "tiny_fixedidx", "tiny_nolocal_n2", "tiny_single_view"]
+
+
+@pytest.mark.parametrize("tag", ALL_TAGS)
 def test_tiny_end_to_end(golden_dir, tag):
     g = torch.load(os.path.join(golden_dir, f"{tag}.pt"))
     enc, dec, head = O.tiny_args()
+    dec.update(g.get("dec_over", {}))
+    head.update(g.get("head_over", {}))
     sd = synth_state_dict(g["shapes"], seed=g["weight_seed"])
     imgs = synth_images(g["N"], g["B"], g["H"], g["W"])
     taps = {}
@@ -36,6 +41,19 @@ def test_tiny_end_to_end(golden_dir, tag):
             assert rel_l2(taps[ok], g["taps"][gk]) < TOL, gk
     if "path3_uncropped" in g["taps"]:
         assert rel_l2(taps["path3"], g["taps"]["path3_uncropped"]) < TOL
+
+
+def test_mixed_resolution_views(golden_dir):
+    g = torch.load(os.path.join(golden_dir, "tiny_mixed_res.pt"))
+    enc, dec, head = O.tiny_args()
+    sd = synth_state_dict(g["shapes"], seed=g["weight_seed"])
+    imgs = [synth_images(1, g["B"], h, w, seed0=1234 + i)[0] for i, (h, w) in enumerate(g["sizes"])]
+    torch.manual_seed(g["rng_seed"])
+    preds = O.forward(sd, enc, dec, head, imgs)
+    for i, (p, q) in enumerate(zip(preds, g["preds"])):
+        for k in q:
+            assert p[k].shape == q[k].shape
+            assert rel_l2(p[k], q[k]) < TOL, (i, k, rel_l2(p[k], q[k]))
 
 
 def test_image_id_rng_stream(golden_dir):
