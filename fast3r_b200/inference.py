@@ -151,9 +151,10 @@ def loss_of_one_batch(batch, model, criterion, device, precision, symmetrize_bat
                       profiling=False):
     """fast3r/dust3r/inference_multiview.py:22-67 (H2D of the view tensors, model call, optional criterion)."""
     device = torch.device(device)
+    sharded = getattr(model, "sp_group", None) is not None  # sequence parallel: the model uploads only its own views
     for view in batch:
         for name in _MOVE_KEYS:
-            if name not in view:
+            if name not in view or (sharded and name == "img"):
                 continue
             src = view[name]
             view[name] = src.to(device, non_blocking=True)

@@ -610,6 +610,8 @@ class Fast3R(nn.Module):
         if not same_shape:
             return self._forward_mixed(views, profiling)
         device = views[0]["img"].device
+        if self.sp_group is not None and device.type != "cuda":
+            device = next(self.parameters()).device  # sharded forward: host views are uploaded per rank below
         P_ = self._pack(device)
         N = len(views)
         B, _, H, W = views[0]["img"].shape
@@ -629,7 +631,8 @@ class Fast3R(nn.Module):
         else:
             lo, hi = sp.view_range(N)
         n_loc = hi - lo
-        imgs = torch.cat([views[i]["img"] for i in range(lo, hi)], dim=0).to(dtype=F32).contiguous()  # (n_loc*B,...)
+        imgs = torch.cat([views[i]["img"].to(device, non_blocking=True) for i in range(lo, hi)],
+                         dim=0).to(dtype=F32).contiguous()  # (n_loc*B, 3, H, W)
 
         feats, P, gh, gw = self._encode(imgs, P_)  # (n_loc*B*P, D), order (n, b, p)
         if profiling:

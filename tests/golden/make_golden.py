@@ -24,7 +24,7 @@ def half(t):
     return t.detach().clone()
 
 
-def run_tiny(B, N, H, W, tag, dec_over=None, head_over=None):
+def run_tiny(B, N, H, W, tag, dec_over=None, head_over=None, train_mode=False):
     enc, dec, head = tiny_args()
     dec.update(dec_over or {})
     head.update(head_over or {})
@@ -33,6 +33,8 @@ def run_tiny(B, N, H, W, tag, dec_over=None, head_over=None):
     shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
     sd = synth_state_dict(shapes, seed=0)
     model.load_state_dict(sd)
+    if train_mode:
+        model.train()  # forward-only check of the training-mode variants (scale 1/8, per-view heads)
     taps = {}
 
     def hook(name):
@@ -68,12 +70,12 @@ def run_tiny(B, N, H, W, tag, dec_over=None, head_over=None):
     torch.manual_seed(7)
     with torch.no_grad():
         preds = model(views)
-    keep = None if (B == 1 and not dec_over and not head_over) else ()
+    keep = None if (B == 1 and not dec_over and not head_over and not train_mode) else ()
     snap = {k: v for k, v in taps.items() if keep is None or k in keep}  # snapshot (later runs re-fire the hooks)
     out = dict(shapes=shapes, taps=snap, image_ids=ids, B=B, N=N, H=H, W=W, weight_seed=0, rng_seed=7,
-               dec_over=dec_over or {}, head_over=head_over or {},
+               dec_over=dec_over or {}, head_over=head_over or {}, train_mode=train_mode,
                preds=[{k: half(v) for k, v in p.items()} for p in preds])
-    if B == 1 and not dec_over and not head_over:
+    if B == 1 and not dec_over and not head_over and not train_mode:
         # the public API on the same inputs (inference(): collate, dtype="32", to_cpu)
         views1 = [dict(img=imgs[i], true_shape=np.int32([[H, W]]), idx=i, instance=str(i),
                        dataset="synthetic", label=f"v{i}") for i in range(N)]
@@ -161,4 +163,5 @@ if __name__ == "__main__":
     run_tiny(1, 2, 32, 48, "tiny_nolocal_n2", head_over=dict(with_local_head=False))
     run_tiny(1, 1, 48, 48, "tiny_single_view")
     run_tiny_mixed()
+    run_tiny(1, 3, 32, 48, "tiny_trainmode", train_mode=True)
     run_blocks()

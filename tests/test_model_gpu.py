@@ -25,12 +25,14 @@ def _build(tag, golden_dir):
     model = Fast3R(enc, dec, head).eval()
     model.load_state_dict(synth_state_dict(g["shapes"], seed=g["weight_seed"]))
     model = model.cuda()
+    if g.get("train_mode", False):
+        model.train()  # forward semantics of training mode (attention scale 1/8); backward is not built
     imgs = synth_images(g["N"], g["B"], g["H"], g["W"])
     return g, model, imgs
 
 
 @pytest.mark.parametrize("tag", ["tiny_b1_n3", "tiny_b2_n2", "tiny_noattnbias", "tiny_fixedidx", "tiny_nolocal_n2",
-                                 "tiny_single_view"])
+                                 "tiny_single_view", "tiny_trainmode"])
 def test_tiny_vs_reference_golden(golden_dir, tag):
     g, model, imgs = _build(tag, golden_dir)
     views = [dict(img=im.cuda(), true_shape=torch.tensor([[g["H"], g["W"]]] * g["B"]), idx=i, instance=str(i))

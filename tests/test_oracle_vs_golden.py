@@ -12,7 +12,8 @@ from tests.golden.synth import synth_state_dict, synth_images
 TOL = 2e-5  # fp32 CPU, different summation order (SDPA-flash vs naive, conv algorithms)
 
 
-ALL_TAGS = ["tiny_b1_n3", "tiny_b2_n2", "tiny_noattnbias", "tiny_fixedidx", "tiny_nolocal_n2", "tiny_single_view"]
+ALL_TAGS = ["tiny_b1_n3", "tiny_b2_n2", "tiny_noattnbias", "tiny_fixedidx", "tiny_nolocal_n2", "tiny_single_view",
+            "tiny_trainmode"]
 
 
 @pytest.mark.parametrize("tag", ALL_TAGS)
@@ -25,7 +26,7 @@ def test_tiny_end_to_end(golden_dir, tag):
     imgs = synth_images(g["N"], g["B"], g["H"], g["W"])
     taps = {}
     torch.manual_seed(g["rng_seed"])  # image ids must come out of the same RNG stream
-    preds = O.forward(sd, enc, dec, head, imgs, taps=taps)
+    preds = O.forward(sd, enc, dec, head, imgs, training=g.get("train_mode", False), taps=taps)
     for i, (p, q) in enumerate(zip(preds, g["preds"])):
         assert sorted(p) == sorted(q)
         for k in q:
