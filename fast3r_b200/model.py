@@ -600,10 +600,17 @@ class Fast3R(nn.Module):
         return final_results
 
     # ---- forward (fast3r/models/fast3r.py:302-497)
-    @torch.no_grad()
     def forward(self, views, profiling=False):
-        if self.training and torch.is_grad_enabled():
-            pass  # backward kernels are not part of this round; forward semantics (train scale 0.125) are honoured
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError(
+                "fast3r_b200.Fast3R has no backward kernels (training step, SURVEY a13 / config 5, is not built): "
+                "call it under torch.no_grad() for a forward-only pass, or use model.eval()")
+        with torch.no_grad():
+            return self._forward(views, profiling)
+
+    def _forward(self, views, profiling=False):
+        # (decorated with no_grad: the CUDA path has no backward kernels yet.  Training-mode FORWARD semantics - attention
+        # scale 1/8, fast3r/croco/models/blocks.py:151-154 - are honoured and tested; optimisation steps are not.)
         profiling_info = {} if profiling else None
         t_start = time.time()
         same_shape = all(v["img"].shape == views[0]["img"].shape for v in views)

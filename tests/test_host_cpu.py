@@ -63,6 +63,13 @@ def test_no_cpu_fallback():
         ops.cast_bf16(torch.zeros(8), torch.zeros(8, dtype=torch.bfloat16))
 
 
+def test_training_step_fails_loudly():
+    from fast3r_b200 import Fast3R, tiny_args
+    m = Fast3R(*tiny_args()).train()
+    with pytest.raises(NotImplementedError, match="backward"):
+        m([dict(img=torch.zeros(1, 3, 32, 32))])
+
+
 def test_collate_like_reference():
     from fast3r_b200.inference import collate_with_cat, to_cpu, check_if_same_size
     views = [dict(img=torch.zeros(1, 3, 16, 32), true_shape=np.int32([[16, 32]]), idx=i, instance=str(i))
