@@ -184,8 +184,8 @@ def run_ours(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     enc, dec, head = vit_large_args()
     torch.manual_seed(0)
-    model = Fast3R(enc, dec, head).eval()
-    model = model.to(dev)
+    with torch.device(dev):  # random-init ViT-L weights created directly in HBM (no checkpoint available offline)
+        model = Fast3R(enc, dec, head).eval()
     sp = None
     if world > 1:
         from fast3r_b200.parallel import enable_sequence_parallel
