@@ -368,6 +368,8 @@ class Fast3R(nn.Module):
         enc = self.encoder
         n, _, H, W = imgs.shape
         gh, gw = H // enc.patch_size, W // enc.patch_size
+        if max(gh, gw) > P_["rope_cos"].shape[0]:
+            raise ValueError(f"image too large for the RoPE table ({gh}x{gw} patches > {P_['rope_cos'].shape[0]})")
         P, D = gh * gw, enc.embed_dim
         feats = torch.empty(n * P, D, dtype=BF16, device=imgs.device)
         chunk = self.max_images_per_encoder_chunk
