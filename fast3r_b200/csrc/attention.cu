@@ -81,6 +81,12 @@ F3R_DEVICE void exp2_emu2(float& e0, float& e1, float x0, float x1) {
 // bit k set: pair k of every 8 score pairs takes the FMA-pipe exp2.  Measured (profiles/r01_notes.md): in the isolated
 // softmax stream 25 % emulation is 12 % faster (2386 -> 2110 clk / iteration), but in the full kernel the decoder layer
 // at N=32 went from 2.70 ms to 2.99 ms, so it is compiled out by default (build with -DF3R_ATT_EMU_MASK=0x11 to try).
+// 1: deferred row max (one-pass softmax, see the loop); 0: classic max pass before the exponentials.
+// Measured at N=32: 3.06 ms per decoder layer vs 2.70 ms for the classic order (the early pv_done wait and the chunked
+// P stores cost more than the max pre-pass saves), so the classic order stays the default.
+#ifndef F3R_ATT_DEFER_MAX
+#define F3R_ATT_DEFER_MAX 0
+#endif
 #ifndef F3R_ATT_EMU_MASK
 #define F3R_ATT_EMU_MASK 0x0
 #endif
@@ -236,7 +242,120 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     float m_used = -INFINITY;  // raw-score reference max the exponentials are taken against
     float l = 0.f;             // this thread's partial row sum
 
+    float mx_prev = -INFINITY;  // (deferred-max variant) raw row max of the previous key block
     for (int j = 0; j < nkv; ++j) {
+      if constexpr (kSplit == 1 && F3R_ATT_DEFER_MAX) {
+        // ---- one-pass variant: the exponentials of block j are taken against the reference max known BEFORE the block
+        // (decided from block j-1's max), so the row-max reduction runs inside the exp loop on the ALU pipe instead of
+        // as a serial pre-pass.  Exact: P_j, l and O always share one reference; the reference moves one block late.
+        // If block j overshoots the reference by more than 2^64 the block is recomputed against its own max.
+        mbar_wait(&s_full[t], j & 1);
+        tc_fence_after();
+        uint32_t s[128];
+        tmem_ld32(tm_s + 0, s + 0);
+        tmem_ld32(tm_s + 32, s + 32);
+        tmem_ld32(tm_s + 64, s + 64);
+        tmem_ld32(tm_s + 96, s + 96);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&s_free[t]);
+        if (j == nkv - 1) {
+          const int valid = p.skv - j * 128;
+          if (valid < 128) {
+#pragma unroll
+            for (int i = 0; i < 128; ++i)
+              if (i >= valid) s[i] = 0xff800000u;
+          }
+        }
+        auto rowmax = [&]() {
+          float a0 = max3(__uint_as_float(s[0]), __uint_as_float(s[1]), __uint_as_float(s[2]));
+          float a1 = max3(__uint_as_float(s[3]), __uint_as_float(s[4]), __uint_as_float(s[5]));
+          float a2 = __uint_as_float(s[6]), a3 = __uint_as_float(s[7]);
+#pragma unroll
+          for (int i = 8; i < 128; i += 8) {
+            a0 = max3(a0, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
+            a1 = max3(a1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
+            a2 = max3(a2, __uint_as_float(s[i + 4]), __uint_as_float(s[i + 5]));
+            a3 = max3(a3, __uint_as_float(s[i + 6]), __uint_as_float(s[i + 7]));
+          }
+          return fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
+        };
+        auto rescale_o = [&](float alpha) {  // O_t *= alpha (PV_{j-1} must have completed)
+          uint32_t o[32];
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            tmem_ld32(tm_o + 32 * c, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st32(tm_o + 32 * c, o);
+          }
+          tmem_st_wait();
+        };
+        if (j == 0) {
+          m_used = rowmax();  // the first block has no earlier reference
+        } else {
+          float alpha = 1.f;
+          const bool need = (mx_prev - m_used) * sl2 > 8.f;
+          if (need) {
+            alpha = ex2_approx((m_used - mx_prev) * sl2);
+            m_used = mx_prev;
+            l *= alpha;
+          }
+          mbar_wait(&pv_done[t], (j - 1) & 1);  // O_t quiescent and P_t consumed (needed before the P stores anyway)
+          tc_fence_after();
+          if (__any_sync(0xffffffffu, need)) rescale_o(alpha);
+        }
+        const float l_before = l;
+        float mxc0, mxc1;
+        auto exp_pass = [&](bool track) {
+          const float nm = -m_used * sl2;
+          float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+          mxc0 = -INFINITY; mxc1 = -INFINITY;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t pk[16];
+#pragma unroll
+            for (int i = 32 * c; i < 32 * c + 32; i += 4) {
+              float x0, x1, x2, x3;
+              ffma2(x0, x1, __uint_as_float(s[i]), __uint_as_float(s[i + 1]), sl2, nm);
+              ffma2(x2, x3, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]), sl2, nm);
+              if (track) {
+                mxc0 = max3(mxc0, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
+                mxc1 = max3(mxc1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
+              }
+              const float e0 = ex2_approx(x0), e1 = ex2_approx(x1), e2 = ex2_approx(x2), e3 = ex2_approx(x3);
+              fadd2(l0, l1, e0, e1);
+              fadd2(l2, l3, e2, e3);
+              pk[(i - 32 * c) / 2] = pack_bf16(e0, e1);
+              pk[(i - 32 * c) / 2 + 1] = pack_bf16(e2, e3);
+            }
+            tmem_st16(tm_p + 16 * c, pk);
+          }
+          return (l0 + l1) + (l2 + l3);
+        };
+        float lsum = exp_pass(j > 0);
+        if (j > 0) {
+          const float mx_cur = fmaxf(mxc0, mxc1);
+          mx_prev = mx_cur;
+          const bool over = (mx_cur - m_used) * sl2 > 64.f;  // reference too stale for this block: redo it exactly
+          if (__any_sync(0xffffffffu, over)) {
+            float alpha = 1.f;
+            if (over) { alpha = ex2_approx((m_used - mx_cur) * sl2); m_used = mx_cur; }
+            l = l_before * alpha;
+            tmem_st_wait();
+            rescale_o(alpha);
+            lsum = exp_pass(false);
+          }
+        } else {
+          mx_prev = m_used;
+        }
+        l += lsum;
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&p_full[t]);
+        continue;
+      }
       mbar_wait(&s_full[t], j & 1);
       tc_fence_after();
       uint32_t s[COLS];
