@@ -70,21 +70,48 @@ __device__ __forceinline__ void prefetch_res(const GemmArgs& p, ResChunk& rc, si
 }
 
 // exact-erf GELU (nn.GELU(), fast3r/croco/models/blocks.py:83) with erf from Abramowitz-Stegun 7.1.26
-// (|abs err| <= 1.5e-7, far below the bf16 rounding of the stored activation); 2 MUFU + ~12 FMA-class ops.
+// (|abs err| <= 1.5e-7, far below the bf16 rounding of the stored activation), evaluated on PAIRS with the packed
+// fp32x2 FMA pipe ops (FFMA2 / FMUL2): per pair 12 packed ops + 4 MUFU (2 rcp, 2 ex2) + 2 sign merges.
+__device__ __forceinline__ void mul2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  asm("{ .reg .b64 ra, rb, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mul.rn.f32x2 rd, ra, rb; mov.b64 {%0,%1}, rd; }"
+      : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void fma2(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) {
+  asm("{ .reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mov.b64 rc, {%6,%7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0,%1}, rd; }"
+      : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
+}
+__device__ __forceinline__ void gelu_fast2(float& x0, float& x1) {
+  float z0, z1;
+  mul2(z0, z1, fabsf(x0), fabsf(x1), 0.70710678118654752440f, 0.70710678118654752440f);
+  float u0, u1;
+  fma2(u0, u1, z0, z1, 0.3275911f, 0.3275911f, 1.0f, 1.0f);
+  float t0, t1;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(u0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(u1));
+  float p0, p1;
+  fma2(p0, p1, t0, t1, 1.061405429f, 1.061405429f, -1.453152027f, -1.453152027f);
+  fma2(p0, p1, p0, p1, t0, t1, 1.421413741f, 1.421413741f);
+  fma2(p0, p1, p0, p1, t0, t1, -0.284496736f, -0.284496736f);
+  fma2(p0, p1, p0, p1, t0, t1, 0.254829592f, 0.254829592f);
+  mul2(p0, p1, p0, p1, t0, t1);
+  float a0, a1;
+  mul2(a0, a1, z0, z1, z0, z1);
+  mul2(a0, a1, a0, a1, -1.4426950408889634f, -1.4426950408889634f);
+  float e0, e1;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
+  float r0, r1;                                   // erf(|z|) = 1 - poly * exp(-z^2)
+  fma2(r0, r1, p0, p1, -e0, -e1, 1.0f, 1.0f);
+  r0 = copysignf(r0, x0); r1 = copysignf(r1, x1);
+  float h0, h1;
+  mul2(h0, h1, x0, x1, 0.5f, 0.5f);
+  fma2(x0, x1, h0, h1, r0, r1, h0, h1);           // 0.5 x (1 + erf)
+}
 __device__ __forceinline__ float gelu_fast(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  float t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  poly *= t;
-  float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * z * z));
-  const float erf_abs = fmaf(-poly, e, 1.0f);
-  const float erf_v = copysignf(erf_abs, x);
-  return 0.5f * x * (1.0f + erf_v);
+  float a = x, b = x;
+  gelu_fast2(a, b);
+  return a;
 }
 
 // Row-domain part: bias, RoPE, image-index embedding, or the FINAL 128->4 dot product.  Returns false if the chunk is
@@ -184,7 +211,7 @@ __device__ __forceinline__ void epilogue_store(const GemmArgs& p, const float (&
     if (p.act == ACT_RELU) {
       x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f);
     } else if (p.act == ACT_GELU) {
-      x0 = gelu_fast(x0); x1 = gelu_fast(x1); x2 = gelu_fast(x2); x3 = gelu_fast(x3);
+      gelu_fast2(x0, x1); gelu_fast2(x2, x3);
     }
     void* base = p.out0;
     size_t o = off;
@@ -216,7 +243,7 @@ __device__ __forceinline__ void epilogue_tma(const GemmArgs& p, float (&v)[32], 
     for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
   } else if (p.act == ACT_GELU) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = gelu_fast(v[i]);
+    for (int i = 0; i < 32; i += 2) gelu_fast2(v[i], v[i + 1]);
   }
   if (lane == 0) tma_store_wait_read();  // the previous tile of this warp has left the staging buffer
   __syncwarp();
