@@ -108,12 +108,6 @@ __device__ __forceinline__ void gelu_fast2(float& x0, float& x1) {
   mul2(h0, h1, x0, x1, 0.5f, 0.5f);
   fma2(x0, x1, h0, h1, r0, r1, h0, h1);           // 0.5 x (1 + erf)
 }
-__device__ __forceinline__ float gelu_fast(float x) {
-  float a = x, b = x;
-  gelu_fast2(a, b);
-  return a;
-}
-
 // Row-domain part: bias, RoPE, image-index embedding, or the FINAL 128->4 dot product.  Returns false if the chunk is
 // fully consumed here (FINAL).
 __device__ __forceinline__ bool epilogue_rows(const GemmArgs& p, float (&v)[32], int m, int col0, bool row_ok,
