@@ -38,6 +38,21 @@ def test_image_id_rng_stream_matches_reference(golden_dir):
     assert torch.equal(m.decoder.image_idx_emb, image_idx_table(128))
 
 
+def test_image_ids_at_the_1000_view_limit():
+    """N = 1000 is the model's maximum (image-index table has 1000 rows, fast3r/models/fast3r.py:694,742)."""
+    from fast3r_b200 import Fast3R, tiny_args
+    from oracle.fast3r_oracle import draw_image_ids
+    m = Fast3R(*tiny_args())
+    torch.manual_seed(3)
+    a = m.decoder.draw_image_ids(2, 1000)
+    torch.manual_seed(3)
+    b = draw_image_ids(2, 1000)
+    assert torch.equal(a, b) and a.shape == (2, 1000)
+    assert sorted(a[0].tolist()) == list(range(1000))  # a permutation: every table row used exactly once
+    with pytest.raises(RuntimeError):
+        m.decoder.draw_image_ids(1, 1001)              # like the reference: randperm(999) cannot fill 1000 slots
+
+
 def test_cabi_exports_every_declared_symbol():
     from fast3r_b200 import lib as L
     from fast3r_b200.build import build
