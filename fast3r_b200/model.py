@@ -228,6 +228,15 @@ def _w_lin2d(m) -> torch.Tensor:  # 1x1 conv (out,in,1,1) -> (out,1,in)
     return w.reshape(w.shape[0], 1, w.shape[1]).to(BF16).contiguous()
 
 
+def _require_cuda(device) -> None:
+    """The product has exactly one compute path: the sm_100a kernels.  (tests/ replace this hook, together with
+    ``fast3r_b200.model.ops``, by a CPU emulator of the C ABI to exercise the host orchestration without a GPU.)"""
+    if device.type != "cuda":
+        raise RuntimeError("fast3r_b200.Fast3R runs on CUDA (sm_100a) only; call model.to('cuda') first. "
+                           "There is no CPU fallback.")
+    L.load()
+
+
 # --------------------------------------------------------------------------- the model
 class Fast3R(nn.Module):
     """Drop-in replacement for fast3r.models.fast3r.Fast3R (same ctor / state_dict / forward contract)."""
@@ -313,10 +322,7 @@ class Fast3R(nn.Module):
         sig = (self._signature(), str(device))
         if self._packed is not None and self._packed_sig == sig:
             return self._packed
-        if device.type != "cuda":
-            raise RuntimeError("fast3r_b200.Fast3R runs on CUDA (sm_100a) only; call model.to('cuda') first. "
-                               "There is no CPU fallback.")
-        L.load()
+        _require_cuda(device)
         enc, dec = self.encoder, self.decoder
         if enc.embed_dim // enc.num_heads != 64 or dec.embed_dim // dec.num_heads != 64:
             raise NotImplementedError("fast3r_b200 attention kernel is specialised for head_dim 64")

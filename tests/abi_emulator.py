@@ -1,0 +1,120 @@
+"""CPU emulator of the fast3r_b200 C ABI (TEST INFRASTRUCTURE ONLY).
+
+An executable specification of what each ``fast3r_b200.ops`` entry point computes, written with plain torch CPU
+ops: same argument meaning, same layouts, same rounding points (bf16 operands, fp32 accumulation, bf16/fp32 outputs).
+tests monkeypatch it over ``fast3r_b200.model.ops`` to run the HOST orchestration (view grouping, batch permutes,
+head chunking, sequence-parallel sharding over gloo, result assembly) without a GPU and compare against the
+reference-generated fixtures.  It is never imported by the product; the product has no CPU path.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+from fast3r_b200 import lib as L
+
+BF16, F32 = torch.bfloat16, torch.float32
+KERNEL_TIMER = None
+
+
+def _store(dst, val):
+    dst.copy_(val.to(dst.dtype).reshape(dst.shape))
+
+
+def gemm(a, wt, *, w, h=1, nb=1, taps=1, bias=None, out0=None, out1=None, res0=None, res1=None, act=L.ACT_NONE,
+         epi=L.EPI_STORE, ldo=None, split_col=0, out0b=None, ldo_b=0, tok_per_img=0, grid_w=0, rope_cols=0,
+         rope_cos=None, rope_sin=None, emb_table=None, emb_ids=None, ct_k=0, ct_cout=0, w4=None, b4=None, pts=None,
+         conf=None):
+    n, k = wt.shape[0], wt.shape[-1]
+    M = nb * h * w
+    A = a.reshape(nb, h, w, k).float()
+    W = wt.reshape(n, taps, k).float()
+    if taps == 1:
+        acc = A.reshape(M, k) @ W[:, 0].T
+    else:  # 3x3, stride 1, zero pad 1; weight layout (out, ky*3+kx, in)
+        wc = W.reshape(n, 3, 3, k).permute(0, 3, 1, 2)
+        acc = F.conv2d(A.permute(0, 3, 1, 2), wc, padding=1).permute(0, 2, 3, 1).reshape(M, n)
+    v = acc
+    if bias is not None:
+        v = v + (bias.float().repeat(n // bias.numel()) if epi == L.EPI_CONVT else bias.float())
+    if epi == L.EPI_ROPE:
+        t = torch.arange(M) % tok_per_img
+        py, px = t // grid_w, t % grid_w
+        v = v.clone()
+        for c0 in range(0, rope_cols, 32):
+            pos = px if (c0 // 32) % 2 else py
+            cs, sn = rope_cos.float()[pos], rope_sin.float()[pos]  # (M,16)
+            x1, x2 = v[:, c0:c0 + 16].clone(), v[:, c0 + 16:c0 + 32].clone()
+            v[:, c0:c0 + 16] = x1 * cs - x2 * sn
+            v[:, c0 + 16:c0 + 32] = x2 * cs + x1 * sn
+    if epi == L.EPI_IDXEMB:
+        rows = emb_ids.long().reshape(-1)
+        if tok_per_img > 0:
+            rows = rows.repeat_interleave(tok_per_img)
+        v = v + emb_table.float()[rows]
+    if epi == L.EPI_FINAL:
+        y = F.relu(v) @ w4.float().T + b4.float()
+        d = y[:, :3].norm(dim=-1, keepdim=True)
+        _store(pts, y[:, :3] / d.clip(min=1e-8) * torch.expm1(d))
+        _store(conf, 1 + y[:, 3].exp())
+        return
+    if epi == L.EPI_CONVT:  # column (i*k+j)*cout + o of pixel (y, x) -> pixel (y*k+i, x*k+j), channel o
+        kk = ct_k
+        v = v.reshape(nb, h, w, kk, kk, ct_cout).permute(0, 1, 3, 2, 4, 5).reshape(nb * h * kk * w * kk, ct_cout)
+    if res0 is not None:
+        v = v + res0.float().reshape(v.shape)
+    if res1 is not None:
+        v = v + res1.float().reshape(v.shape)
+    if out1 is not None:
+        _store(out1, F.relu(v))
+    if out0 is None:
+        return
+    if act == L.ACT_RELU:
+        v = F.relu(v)
+    elif act == L.ACT_GELU:
+        v = F.gelu(v)
+    if split_col > 0:
+        _store(out0, v[:, :split_col])
+        _store(out0b, v[:, split_col:])
+    else:
+        _store(out0, v)
+
+
+def linear(a, wt, bias=None, **kw):
+    return gemm(a, wt, w=a.numel() // a.shape[-1], bias=bias, **kw)
+
+
+def attention(q, kv, out, *, batch, heads, sq, skv, scale, lse=None):
+    D = heads * 64
+    qh = q.reshape(batch, sq, heads, 64).transpose(1, 2).float()
+    kh = kv[:, :D].reshape(batch, skv, heads, 64).transpose(1, 2).float()
+    vh = kv[:, D:].reshape(batch, skv, heads, 64).transpose(1, 2).float()
+    s = (qh @ kh.transpose(-2, -1)) * scale
+    o = s.softmax(-1) @ vh
+    _store(out, o.transpose(1, 2).reshape(batch * sq, D))
+    if lse is not None:
+        _store(lse, torch.logsumexp(s, -1))
+
+
+def layernorm(x, w, b, eps, out):
+    _store(out, F.layer_norm(x.float(), (x.shape[-1],), w.float(), b.float(), eps))
+
+
+def im2col_patch(img, out):
+    n = img.shape[0]
+    _store(out, F.unfold(img.float(), kernel_size=16, stride=16).transpose(1, 2).reshape(-1, 768))
+
+
+def im2col3x3s2(x, out, n, h, w, c, ho, wo):
+    u = F.unfold(x.reshape(n, h, w, c).float().permute(0, 3, 1, 2), kernel_size=3, stride=2, padding=1)
+    _store(out, u.reshape(n, c, 9, ho * wo).permute(0, 3, 2, 1).reshape(n * ho * wo, 9 * c))
+
+
+def upsample2x(x, out, n, h, w, c, ho, wo):
+    r = F.interpolate(x.reshape(n, h, w, c).float().permute(0, 3, 1, 2), scale_factor=2, mode="bilinear",
+                      align_corners=True)
+    _store(out, r[:, :, :ho, :wo].permute(0, 2, 3, 1))
+
+
+def cast_bf16(x, out):
+    _store(out, x)
