@@ -16,24 +16,29 @@ _MOVE_KEYS = "img pts3d valid_mask camera_pose camera_intrinsics F_matrix corres
 _KEEP_HOST_REFS = False  # set by inference() around its loss_of_one_batch call
 
 
+def _map_leaves(obj, leaf_fn):
+    """Applies leaf_fn to every non-container leaf of a nested dict / list / tuple structure (structure preserved)."""
+    if isinstance(obj, dict):
+        return {key: _map_leaves(val, leaf_fn) for key, val in obj.items()}
+    if isinstance(obj, (list, tuple)):
+        return type(obj)(_map_leaves(val, leaf_fn) for val in obj)
+    return leaf_fn(obj)
+
+
 def todevice(batch, device, callback=None, non_blocking=False):
-    """fast3r/dust3r/utils/device.py:14-49."""
+    """Behaviour of fast3r/dust3r/utils/device.py:14-49: move every tensor / ndarray leaf to ``device``
+    ("numpy" converts tensors to ndarrays instead); other leaves pass through."""
     if callback:
         batch = callback(batch)
-    if isinstance(batch, dict):
-        return {k: todevice(v, device) for k, v in batch.items()}
-    if isinstance(batch, (tuple, list)):
-        return type(batch)(todevice(x, device) for x in batch)
-    x = batch
-    if device == "numpy":
-        if isinstance(x, torch.Tensor):
-            x = x.detach().cpu().numpy()
-    elif x is not None:
-        if isinstance(x, np.ndarray):
-            x = torch.from_numpy(x)
-        if torch.is_tensor(x):
-            x = x.to(device, non_blocking=non_blocking)
-    return x
+
+    def move(leaf):
+        if device == "numpy":
+            return leaf.detach().cpu().numpy() if isinstance(leaf, torch.Tensor) else leaf
+        if isinstance(leaf, np.ndarray):
+            leaf = torch.from_numpy(leaf)
+        return leaf.to(device, non_blocking=non_blocking) if torch.is_tensor(leaf) else leaf
+
+    return _map_leaves(batch, move)
 
 
 def to_cpu(x):
@@ -44,35 +49,36 @@ def listify(elems):
     return [x for e in elems for x in e]
 
 
+def _stack_arrays(samples, lists):
+    """Tensors / ndarrays of the samples of one field: concatenated along dim 0 (or flattened into a list).
+    A one-sample "batch" (what inference() builds) is returned as is instead of torch.cat([x]): same values, but no
+    2.26 MB host copy per view, and the caller's page-locked buffers stay page-locked for the async H2D."""
+    tensors = [torch.from_numpy(x) if isinstance(x, np.ndarray) else x for x in samples]
+    if lists:
+        return listify(tensors)
+    return tensors[0] if len(tensors) == 1 else torch.cat(tensors)
+
+
 def collate_with_cat(whatever, lists=False):
-    """fast3r/dust3r/utils/device.py:60-91."""
+    """Behaviour of fast3r/dust3r/utils/device.py:60-91: merge a sequence of samples field by field.  The first sample
+    decides how a field is merged: None -> None; python scalars / strings -> the sequence itself; tuples -> merged
+    column-wise; dicts -> merged key-wise; tensors / ndarrays -> concatenated; anything else -> sequences chained."""
     if isinstance(whatever, dict):
-        return {k: collate_with_cat(vals, lists=lists) for k, vals in whatever.items()}
-    elif isinstance(whatever, (tuple, list)):
-        if len(whatever) == 0:
-            return whatever
-        elem = whatever[0]
-        T = type(whatever)
-        if elem is None:
-            return None
-        if isinstance(elem, (bool, float, int, str)):
-            return whatever
-        if isinstance(elem, tuple):
-            return T(collate_with_cat(x, lists=lists) for x in zip(*whatever))
-        if isinstance(elem, dict):
-            return {k: collate_with_cat([e[k] for e in whatever], lists=lists) for k in elem}
-        # a one-sample "batch" (what inference() builds) is returned as is instead of torch.cat([x]): same values, but
-        # no 2.26 MB host copy per view and the caller's page-locked buffers stay page-locked for the async H2D
-        if isinstance(elem, torch.Tensor):
-            if lists:
-                return listify(whatever)
-            return whatever[0] if len(whatever) == 1 else torch.cat(whatever)
-        if isinstance(elem, np.ndarray):
-            if lists:
-                return listify(whatever)
-            ts = [torch.from_numpy(x) for x in whatever]
-            return ts[0] if len(ts) == 1 else torch.cat(ts)
-        return sum(whatever, T())
+        return {key: collate_with_cat(vals, lists=lists) for key, vals in whatever.items()}
+    if not isinstance(whatever, (tuple, list)) or len(whatever) == 0:
+        return whatever
+    first, seq_type = whatever[0], type(whatever)
+    if first is None:
+        return None
+    if isinstance(first, (bool, float, int, str)):
+        return whatever
+    if isinstance(first, tuple):
+        return seq_type(collate_with_cat(column, lists=lists) for column in zip(*whatever))
+    if isinstance(first, dict):
+        return {key: collate_with_cat([sample[key] for sample in whatever], lists=lists) for key in first}
+    if isinstance(first, (torch.Tensor, np.ndarray)):
+        return _stack_arrays(whatever, lists)
+    return sum(whatever, seq_type())
 
 
 def check_if_same_size(imgs):
