@@ -64,10 +64,11 @@ int make_tmap(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, c
 }
 
 int num_sms() {
-  static int n = 0;
-  if (n) return n;
+  static int cache[64] = {0};  // per device: one process may drive several GPUs
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  int& n = cache[dev & 63];
+  if (n) return n;
   if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
   return n;
 }
@@ -231,10 +232,10 @@ int f3r_layernorm(const float* x, const float* w, const float* b, void* out, int
                "f3r_layernorm (dim must be one of 128,256,384,512,768,1024)");
 }
 
-int f3r_im2col_patch(const float* img, void* out, int32_t n, int32_t h, int32_t w, void* stream) {
+int f3r_im2col_patch(const float* img, void* out, int32_t out_f32, int32_t n, int32_t h, int32_t w, void* stream) {
   if (!img || !out) return fail("f3r_im2col_patch: null operand");
   g_launches++;
-  return check(f3r::launch_im2col_patch(img, out, n, h, w, 16, static_cast<cudaStream_t>(stream)),
+  return check(f3r::launch_im2col_patch(img, out, out_f32, n, h, w, 16, static_cast<cudaStream_t>(stream)),
                "f3r_im2col_patch");
 }
 
@@ -246,13 +247,82 @@ int f3r_im2col3x3s2(const void* in, void* out, int32_t n, int32_t h, int32_t w, 
                "f3r_im2col3x3s2");
 }
 
-int f3r_upsample2x(const void* in, void* out, int32_t n, int32_t h, int32_t w, int32_t c, int32_t ho, int32_t wo,
-                   void* stream) {
+int f3r_upsample2x(const void* in, void* out, int32_t f32, int32_t n, int32_t h, int32_t w, int32_t c, int32_t ho,
+                   int32_t wo, void* stream) {
   if (!in || !out) return fail("f3r_upsample2x: null operand");
   if (ho > 2 * h || wo > 2 * w) return fail("f3r_upsample2x: window larger than the x2 output");
   g_launches++;
-  return check(f3r::launch_upsample2x(in, out, n, h, w, c, ho, wo, 2 * h, 2 * w, static_cast<cudaStream_t>(stream)),
+  return check(f3r::launch_upsample2x(in, out, f32, n, h, w, c, ho, wo, 2 * h, 2 * w,
+                                      static_cast<cudaStream_t>(stream)),
                "f3r_upsample2x");
+}
+
+int f3r_split3(const float* in, void* out, size_t rows, int32_t k, int32_t relu, void* stream) {
+  if (!in || !out) return fail("f3r_split3: null operand");
+  if (k <= 0 || k % 8) return fail("f3r_split3: k=%d must be a positive multiple of 8", k);
+  g_launches++;
+  return check(f3r::launch_split3(in, out, rows, k, relu, static_cast<cudaStream_t>(stream)), "f3r_split3");
+}
+
+int f3r_add_f32(float* dst, const float* src, size_t count, void* stream) {
+  if (!dst || !src) return fail("f3r_add_f32: null operand");
+  g_launches++;
+  return check(f3r::launch_add_f32(dst, src, count, static_cast<cudaStream_t>(stream)), "f3r_add_f32");
+}
+
+size_t f3r_attention_x3_workspace(int32_t batch, int32_t heads, int32_t sq, int32_t skv) {
+  // q3 [batch*sq, heads*192] + k3 [batch*skv, heads*192] + v2 [batch*skv, heads*128] bf16, each 256-byte aligned
+  auto al = [](size_t b) { return (b + 255) & ~static_cast<size_t>(255); };
+  return al(static_cast<size_t>(batch) * sq * heads * 192 * 2) + al(static_cast<size_t>(batch) * skv * heads * 192 * 2) +
+         al(static_cast<size_t>(batch) * skv * heads * 128 * 2);
+}
+
+int f3r_attention_x3(const float* q, int32_t ldq, const float* kv, int32_t ldkv, float* out, int32_t ldo, float* lse,
+                     void* workspace, size_t workspace_bytes, int32_t batch, int32_t heads, int32_t sq, int32_t skv,
+                     float scale, void* stream) {
+  if (!q || !kv || !out || !workspace) return fail("f3r_attention_x3: null operand");
+  if (batch <= 0 || heads <= 0 || sq <= 0 || skv <= 0) return fail("f3r_attention_x3: bad shape");
+  if (ldq % 4 || ldkv % 4 || ldo % 4 || ldq < heads * 64 || ldkv < 2 * heads * 64 || ldo < heads * 64)
+    return fail("f3r_attention_x3: bad leading dimensions");
+  if (workspace_bytes < f3r_attention_x3_workspace(batch, heads, sq, skv))
+    return fail("f3r_attention_x3: workspace too small (%zu < %zu bytes)", workspace_bytes,
+                f3r_attention_x3_workspace(batch, heads, sq, skv));
+  if (reinterpret_cast<uintptr_t>(workspace) & 255) return fail("f3r_attention_x3: workspace not 256-byte aligned");
+  auto al = [](size_t b) { return (b + 255) & ~static_cast<size_t>(255); };
+  uint8_t* w = static_cast<uint8_t*>(workspace);
+  void* q3 = w;
+  void* k3 = w + al(static_cast<size_t>(batch) * sq * heads * 192 * 2);
+  void* v2 = static_cast<uint8_t*>(k3) + al(static_cast<size_t>(batch) * skv * heads * 192 * 2);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  g_launches++;
+  if (check(f3r::launch_attn_split(q, ldq, kv, ldkv, q3, k3, v2, static_cast<size_t>(batch) * sq,
+                                   static_cast<size_t>(batch) * skv, heads, st), "f3r_attention_x3 (split)"))
+    return 1;
+  CUtensorMap tq3, tk3, tv2;
+  const uint32_t box[3] = {64, 128, 1};
+  {
+    const uint64_t dims[3] = {static_cast<uint64_t>(heads) * 192, static_cast<uint64_t>(sq), static_cast<uint64_t>(batch)};
+    const uint64_t str[2] = {static_cast<uint64_t>(heads) * 192 * 2, static_cast<uint64_t>(heads) * 192 * 2 * sq};
+    if (make_tmap(&tq3, q3, 3, dims, str, box)) return 1;
+  }
+  {
+    const uint64_t dims[3] = {static_cast<uint64_t>(heads) * 192, static_cast<uint64_t>(skv), static_cast<uint64_t>(batch)};
+    const uint64_t str[2] = {static_cast<uint64_t>(heads) * 192 * 2, static_cast<uint64_t>(heads) * 192 * 2 * skv};
+    if (make_tmap(&tk3, k3, 3, dims, str, box)) return 1;
+  }
+  {
+    const uint64_t dims[3] = {static_cast<uint64_t>(heads) * 128, static_cast<uint64_t>(skv), static_cast<uint64_t>(batch)};
+    const uint64_t str[2] = {static_cast<uint64_t>(heads) * 128 * 2, static_cast<uint64_t>(heads) * 128 * 2 * skv};
+    if (make_tmap(&tv2, v2, 3, dims, str, box)) return 1;
+  }
+  f3r::AttnArgs a;
+  memset(&a, 0, sizeof(a));
+  a.batch = batch; a.heads = heads; a.sq = sq; a.skv = skv;
+  a.q_tiles = (sq + 127) / 128;
+  a.scale_log2 = scale * 1.4426950408889634f;
+  a.ldo = ldo; a.out = out; a.lse = lse;
+  g_launches++;
+  return check(f3r::launch_attention_x3(tq3, tk3, tv2, a, st), "f3r_attention_x3");
 }
 
 int f3r_cast_bf16(const float* in, void* out, size_t count, void* stream) {

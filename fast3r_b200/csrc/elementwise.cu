@@ -74,7 +74,8 @@ cudaError_t launch_layernorm(const float* x, const float* w, const float* b, voi
 // ---------------------------------------------------------------- patch im2col
 // img fp32 (n,3,H,W) -> bf16 [n*(H/p)*(W/p), 3*p*p], k = c*p*p + ky*p + kx (Conv2d weight flattening,
 // fast3r/croco/models/blocks.py:412-414), token order y*gw + x (patch_embed.py:30-33).  p == 16.
-__global__ void __launch_bounds__(256) im2col_patch_kernel(const float* __restrict__ img, uint4* __restrict__ out,
+template <bool kF32>
+__global__ void __launch_bounds__(256) im2col_patch_kernel(const float* __restrict__ img, void* __restrict__ out_,
                                                            int n, int H, int W) {
   const int gh = H / 16, gw = W / 16;
   const size_t total = static_cast<size_t>(n) * gh * gw * 96;  // 768 / 8 vectors per token
@@ -88,18 +89,25 @@ __global__ void __launch_bounds__(256) im2col_patch_kernel(const float* __restri
     const float4* src = reinterpret_cast<const float4*>(
         img + ((im * 3 + c) * H + gy * 16 + ky) * static_cast<size_t>(W) + gx * 16 + kx0);
     const float4 a = __ldg(src), b = __ldg(src + 1);
-    uint4 o;
-    o.x = pack_bf16(a.x, a.y); o.y = pack_bf16(a.z, a.w);
-    o.z = pack_bf16(b.x, b.y); o.w = pack_bf16(b.z, b.w);
-    out[idx] = o;
+    if constexpr (kF32) {  // parity mode: the GEMM operand is hi/lo-split later
+      float4* out = static_cast<float4*>(out_);
+      out[2 * idx] = a; out[2 * idx + 1] = b;
+    } else {
+      uint4 o;
+      o.x = pack_bf16(a.x, a.y); o.y = pack_bf16(a.z, a.w);
+      o.z = pack_bf16(b.x, b.y); o.w = pack_bf16(b.z, b.w);
+      static_cast<uint4*>(out_)[idx] = o;
+    }
   }
 }
-cudaError_t launch_im2col_patch(const float* img, void* out, int n, int H, int W, int patch, cudaStream_t stream) {
+cudaError_t launch_im2col_patch(const float* img, void* out, int out_f32, int n, int H, int W, int patch,
+                                cudaStream_t stream) {
   if (patch != 16 || H % 16 || W % 16) return cudaErrorInvalidValue;
   const size_t total = static_cast<size_t>(n) * (H / 16) * (W / 16) * 96;
   if (total == 0) return cudaSuccess;
   const int grid = static_cast<int>(total / 256 + 1 < 148 * 16 ? total / 256 + 1 : 148 * 16);
-  im2col_patch_kernel<<<grid, 256, 0, stream>>>(img, static_cast<uint4*>(out), n, H, W);
+  if (out_f32) im2col_patch_kernel<true><<<grid, 256, 0, stream>>>(img, out, n, H, W);
+  else im2col_patch_kernel<false><<<grid, 256, 0, stream>>>(img, out, n, H, W);
   return cudaGetLastError();
 }
 
@@ -167,9 +175,49 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const uint4* __restrict
   }
   out[((im * Ho + oy) * Wo + ox) * C8 + c] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
 }
-cudaError_t launch_upsample2x(const void* in, void* out, int n, int H, int W, int C, int Ho, int Wo, int Hfull,
+// fp32 NHWC variant (parity mode): one float4 (4 channels) per thread
+__global__ void __launch_bounds__(256) upsample2x_f32_kernel(const float4* __restrict__ in, float4* __restrict__ out,
+                                                             int H, int W, int C4, int c4_shift, int Ho, int Wo, float sy,
+                                                             float sx) {
+  const int oy = blockIdx.y;
+  const size_t im = blockIdx.z;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= Wo * C4) return;
+  const int c = t & (C4 - 1), ox = t >> c4_shift;
+  const float fy = sy * oy, fx = sx * ox;
+  const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
+  const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+  const float ly = fy - y0, lx = fx - x0;
+  const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+  const float4* base = in + im * H * W * C4 + c;
+  const float4 a = __ldg(base + (static_cast<size_t>(y0) * W + x0) * C4);
+  const float4 b = __ldg(base + (static_cast<size_t>(y0) * W + x1) * C4);
+  const float4 d = __ldg(base + (static_cast<size_t>(y1) * W + x0) * C4);
+  const float4 e = __ldg(base + (static_cast<size_t>(y1) * W + x1) * C4);
+  float4 o;
+  o.x = w00 * a.x + w01 * b.x + w10 * d.x + w11 * e.x;
+  o.y = w00 * a.y + w01 * b.y + w10 * d.y + w11 * e.y;
+  o.z = w00 * a.z + w01 * b.z + w10 * d.z + w11 * e.z;
+  o.w = w00 * a.w + w01 * b.w + w10 * d.w + w11 * e.w;
+  out[((im * Ho + oy) * Wo + ox) * C4 + c] = o;
+}
+cudaError_t launch_upsample2x(const void* in, void* out, int f32, int n, int H, int W, int C, int Ho, int Wo, int Hfull,
                               int Wfull, cudaStream_t stream) {
   if (C % 8 || Hfull < 2 || Wfull < 2) return cudaErrorInvalidValue;
+  if (f32) {
+    const int C4 = C / 4;
+    int shift = 0;
+    while ((1 << shift) < C4) ++shift;
+    if ((1 << shift) != C4) return cudaErrorInvalidValue;
+    if (n <= 0 || Ho <= 0 || Wo <= 0) return cudaSuccess;
+    if (n > 65535 || Ho > 65535) return cudaErrorInvalidValue;
+    const float sy = static_cast<float>(H - 1) / static_cast<float>(Hfull - 1);
+    const float sx = static_cast<float>(W - 1) / static_cast<float>(Wfull - 1);
+    dim3 grid((Wo * C4 + 255) / 256, Ho, n);
+    upsample2x_f32_kernel<<<grid, 256, 0, stream>>>(static_cast<const float4*>(in), static_cast<float4*>(out), H, W, C4,
+                                                    shift, Ho, Wo, sy, sx);
+    return cudaGetLastError();
+  }
   const int C8 = C / 8;
   int shift = 0;
   while ((1 << shift) < C8) ++shift;

@@ -51,13 +51,22 @@ struct AttnArgs {
 };
 cudaError_t launch_attention(const CUtensorMap& tq, const CUtensorMap& tkv, const AttnArgs& a, cudaStream_t stream);
 
+// parity mode (attention_x3.cu): hi/lo-split bf16 operands, fp32 out (AttnArgs.out is float*, q_tiles = ceil(sq / 128))
+cudaError_t launch_attention_x3(const CUtensorMap& tq3, const CUtensorMap& tk3, const CUtensorMap& tv2,
+                                const AttnArgs& a, cudaStream_t stream);
+cudaError_t launch_attn_split(const float* q, int ldq, const float* kv, int ldkv, void* q3, void* k3, void* v2,
+                              size_t rows_q, size_t rows_kv, int heads, cudaStream_t stream);
+cudaError_t launch_split3(const float* in, void* out, size_t rows, int k, int relu, cudaStream_t stream);
+cudaError_t launch_add_f32(float* dst, const float* src, size_t n, cudaStream_t stream);
+
 cudaError_t launch_layernorm(const float* x, const float* w, const float* b, void* out, int out_f32, int rows,
                              int dim, float eps, cudaStream_t stream);
-cudaError_t launch_im2col_patch(const float* img, void* out, int n, int H, int W, int patch, cudaStream_t stream);
+cudaError_t launch_im2col_patch(const float* img, void* out, int out_f32, int n, int H, int W, int patch,
+                                cudaStream_t stream);
 cudaError_t launch_im2col3x3s2(const void* in, void* out, int n, int H, int W, int C, int Ho, int Wo,
                                cudaStream_t stream);
-cudaError_t launch_upsample2x(const void* in, void* out, int n, int H, int W, int C, int Ho, int Wo, int Hfull,
-                              int Wfull, cudaStream_t stream);
+cudaError_t launch_upsample2x(const void* in, void* out, int f32, int n, int H, int W, int C, int Ho, int Wo,
+                              int Hfull, int Wfull, cudaStream_t stream);
 cudaError_t launch_cast_bf16(const float* in, void* out, size_t n, cudaStream_t stream);
 
 }  // namespace f3r

@@ -2,10 +2,15 @@
 collation helpers fast3r/dust3r/utils/device.py:52-95).  Same signatures, same result structure
 ``{"views": [...], "preds": [...], "loss": None}`` moved to CPU, same optional ``profiling_info``.
 
-Precision mapping: the reference only disables autocast for the *string* "32"; any other value
-selects an autocast dtype.  This implementation has ONE numeric path (bf16 tensor-core operands, fp32
-accumulation / residual stream / statistics, fp32 outputs), which is at least as close to the reference's fp32
-result as the reference's own bf16-autocast path, so every ``dtype`` value maps onto it and preds come back fp32.
+Precision mapping (reference: inference_multiview.py:41-49).  The reference disables autocast only
+for the *string* "32" (true fp32); ``torch.bfloat16`` selects bf16 autocast and anything else the default autocast
+dtype.  Here:
+  * ``"32"`` and ``torch.float32`` -> the parity path (``precision="fp32"``: fp32 activations, hi/lo-split bf16
+    tensor-core products; ~1e-5 rel-L2 of the reference's fp32 result).  ``torch.float32`` is what README/demo pass
+    and clearly intend fp32, although the reference then silently runs its default autocast dtype (Q1).
+  * everything else (``torch.bfloat16``, "bf16", "16", ...) -> the fast path (``precision="bf16"``: bf16 operands,
+    fp32 accumulation / residual stream / statistics), closer to fp32 than the reference's own bf16-autocast path.
+Preds always come back fp32.
 """
 from __future__ import annotations
 
@@ -93,6 +98,9 @@ class _HostSink:
 
     def __init__(self, device):
         self.host = {}  # device storage ptr -> pinned uint8 host buffer of the same size
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.device = device
         key = (device.type, device.index)
         if key not in _HostSink._streams:
             _HostSink._streams[key] = torch.cuda.Stream(device=device)
@@ -100,7 +108,7 @@ class _HostSink:
 
     def chunk_done(self, tensors, start, count):
         ev = torch.cuda.Event()
-        ev.record()
+        ev.record(torch.cuda.current_stream(self.device))  # the stream the head kernels of this chunk were enqueued on
         self.stream.wait_event(ev)
         with torch.cuda.stream(self.stream):
             for t in tensors:
@@ -132,14 +140,17 @@ def _preds_to_cpu(preds, prefilled=None):
     if not groups:
         return to_cpu(preds)
     host = dict(prefilled or {})
+    devices = set()
     for key, (st, dev) in groups.items():
+        devices.add(dev)
         if key in host:
             continue  # already streamed to the host chunk by chunk during the forward
         dev_bytes = torch.empty(0, dtype=torch.uint8, device=dev).set_(st)
         h = torch.empty(dev_bytes.numel(), dtype=torch.uint8, pin_memory=True)
         h.copy_(dev_bytes, non_blocking=True)
         host[key] = h
-    torch.cuda.current_stream().synchronize()
+    for dev in devices:
+        torch.cuda.current_stream(dev).synchronize()
     out = []
     for p in preds:
         q = {}
@@ -153,9 +164,31 @@ def _preds_to_cpu(preds, prefilled=None):
     return out
 
 
+def precision_of(dtype) -> str:
+    """Kernel precision for an ``inference(dtype=...)`` / ``loss_of_one_batch(precision=...)`` value (module docstring)."""
+    if dtype == "32" or dtype is torch.float32 or dtype == "fp32" or dtype == "float32":
+        return "fp32"
+    return "bf16"
+
+
+class _precision_scope:
+    def __init__(self, model, dtype):
+        self.model, self.want = model, precision_of(dtype)
+
+    def __enter__(self):
+        self.prev = getattr(self.model, "precision", None)
+        if self.prev is not None:
+            self.model.precision = self.want
+
+    def __exit__(self, *exc):
+        if self.prev is not None:
+            self.model.precision = self.prev
+
+
 def loss_of_one_batch(batch, model, criterion, device, precision, symmetrize_batch=False, use_amp=False, ret=None,
                       profiling=False):
-    """fast3r/dust3r/inference_multiview.py:22-67 (H2D of the view tensors, model call, optional criterion)."""
+    """fast3r/dust3r/inference_multiview.py:22-67 (H2D of the view tensors, precision selection, model call, optional
+    criterion)."""
     device = torch.device(device)
     sharded = getattr(model, "sp_group", None) is not None  # sequence parallel: the model uploads only its own views
     for view in batch:
@@ -167,10 +200,11 @@ def loss_of_one_batch(batch, model, criterion, device, precision, symmetrize_bat
             if _KEEP_HOST_REFS and src.device.type == "cpu" and device.type != "cpu":
                 view.setdefault("_host_copy", {})[name] = src  # lets inference() hand the same host tensor back
     views = batch
-    if profiling:
-        preds, profiling_info = model(views, profiling=profiling)
-    else:
-        preds = model(views, profiling=profiling)
+    with _precision_scope(model, precision):
+        if profiling:
+            preds, profiling_info = model(views, profiling=profiling)
+        else:
+            preds = model(views, profiling=profiling)
     loss = criterion(views, preds) if criterion is not None else None
     result = dict(views=views, preds=preds, loss=loss)
     if profiling:
@@ -203,7 +237,8 @@ def inference(multiple_views_in_one_sample, model, device, dtype, verbose=True, 
     if profiling and "profiling_info" in res:
         profiling_info = res.pop("profiling_info")
     # views: the reference copies the (just uploaded) inputs back to the host (to_cpu(res), :92); the bytes are
-    # identical to the caller's host tensors, so those are returned instead of a second PCIe transfer.
+    # identical to the caller's host tensors, so those are returned instead of a second PCIe transfer.  NOTE: the
+    # returned result["views"][i]["img"] therefore ALIASES the caller's input tensor (the reference returns a copy).
     views_cpu = []
     for view in res["views"]:
         host = view.pop("_host_copy", {})

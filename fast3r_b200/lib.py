@@ -36,8 +36,10 @@ class GemmDesc(C.Structure):
     ]
 
 
-EXPORTS = ["f3r_last_error", "f3r_abi_version", "f3r_gemm_desc_size", "f3r_launch_count", "f3r_gemm", "f3r_attention", "f3r_layernorm",
-           "f3r_im2col_patch", "f3r_im2col3x3s2", "f3r_upsample2x", "f3r_cast_bf16"]
+ABI_VERSION = 2
+EXPORTS = ["f3r_last_error", "f3r_abi_version", "f3r_gemm_desc_size", "f3r_launch_count", "f3r_gemm", "f3r_attention",
+           "f3r_layernorm", "f3r_im2col_patch", "f3r_im2col3x3s2", "f3r_upsample2x", "f3r_cast_bf16", "f3r_split3",
+           "f3r_add_f32", "f3r_attention_x3_workspace", "f3r_attention_x3"]
 
 _lib = None
 
@@ -60,17 +62,24 @@ def load() -> C.CDLL:
                                   C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p]
     lib.f3r_layernorm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                   C.c_float, C.c_void_p]
-    lib.f3r_im2col_patch.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+    lib.f3r_im2col_patch.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
     lib.f3r_im2col3x3s2.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                     C.c_int32, C.c_void_p]
     lib.f3r_upsample2x.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
-                                   C.c_int32, C.c_void_p]
+                                   C.c_int32, C.c_int32, C.c_void_p]
+    lib.f3r_split3.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int32, C.c_int32, C.c_void_p]
+    lib.f3r_add_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.f3r_attention_x3_workspace.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32]
+    lib.f3r_attention_x3_workspace.restype = C.c_size_t
+    lib.f3r_attention_x3.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
+                                     C.c_void_p, C.c_size_t, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float,
+                                     C.c_void_p]
     lib.f3r_cast_bf16.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     for name in ("f3r_gemm", "f3r_attention", "f3r_layernorm", "f3r_im2col_patch", "f3r_im2col3x3s2",
-                 "f3r_upsample2x", "f3r_cast_bf16"):
+                 "f3r_upsample2x", "f3r_cast_bf16", "f3r_split3", "f3r_add_f32", "f3r_attention_x3"):
         getattr(lib, name).restype = C.c_int
     lib.f3r_gemm_desc_size.restype = C.c_size_t
-    if lib.f3r_abi_version() != 1 or lib.f3r_gemm_desc_size() != C.sizeof(GemmDesc):
+    if lib.f3r_abi_version() != ABI_VERSION or lib.f3r_gemm_desc_size() != C.sizeof(GemmDesc):
         raise RuntimeError("libfast3r_b200.so ABI mismatch (rebuild: python -m fast3r_b200.build --force)")
     _lib = lib
     return lib

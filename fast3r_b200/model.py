@@ -168,20 +168,37 @@ class PixelwiseTaskWithDPT(nn.Module):
         self.dpt = _DPT(dim_tokens, num_channels=num_channels)
 
 
-# --------------------------------------------------------------------------- packed (device, bf16) weights
-def _w_lin(m) -> torch.Tensor:
-    return m.weight.detach().to(BF16).contiguous().reshape(m.weight.shape[0], 1, -1)
+# --------------------------------------------------------------------------- packed (device) weights
+# Every GEMM weight is packed as [N_out, taps, K] with K contiguous (include/fast3r_b200.h).  Fast path: bf16.
+# Parity path ("fp32"): [Whi | Whi | Wlo] along K (3K wide), matching the [hi | lo | hi] split of the activation, so
+# the same kernel accumulates hi*hi + lo*hi + hi*lo in fp32 (fp32-level products on the bf16 tensor pipe).
+def _pk(w: torch.Tensor, x3: bool) -> torch.Tensor:
+    w = w.detach().to(F32)
+    hi = w.to(BF16)
+    if not x3:
+        return hi.contiguous()
+    lo = (w - hi.float()).to(BF16)
+    return torch.cat([hi, hi, lo], dim=-1).contiguous()
 
 
-def _w_conv3(m) -> torch.Tensor:  # (out,in,3,3) -> (out, 9, in)
+def _w_lin(m, x3=False) -> torch.Tensor:
+    return _pk(m.weight.detach().reshape(m.weight.shape[0], 1, -1), x3)
+
+
+def _w_conv3(m, x3=False) -> torch.Tensor:  # (out,in,3,3) -> (out, 9, in)
     w = m.weight.detach()
-    return w.permute(0, 2, 3, 1).reshape(w.shape[0], 9, w.shape[1]).to(BF16).contiguous()
+    return _pk(w.permute(0, 2, 3, 1).reshape(w.shape[0], 9, w.shape[1]), x3)
 
 
-def _w_convt(m) -> torch.Tensor:  # (in,out,k,k) -> ((i*k+j)*out + o, 1, in)
+def _w_convt(m, x3=False) -> torch.Tensor:  # (in,out,k,k) -> ((i*k+j)*out + o, 1, in)
     w = m.weight.detach()
     k = w.shape[2]
-    return w.permute(2, 3, 1, 0).reshape(k * k * w.shape[1], 1, w.shape[0]).to(BF16).contiguous()
+    return _pk(w.permute(2, 3, 1, 0).reshape(k * k * w.shape[1], 1, w.shape[0]), x3)
+
+
+def _w_lin2d(m, x3=False) -> torch.Tensor:  # 1x1 conv (out,in,1,1) -> (out,1,in)
+    w = m.weight.detach()
+    return _pk(w.reshape(w.shape[0], 1, w.shape[1]), x3)
 
 
 def _f32(t) -> Optional[torch.Tensor]:
@@ -189,43 +206,43 @@ def _f32(t) -> Optional[torch.Tensor]:
 
 
 class _BlockW:
-    def __init__(self, blk: _Block):
+    def __init__(self, blk: _Block, x3=False):
         self.n1w, self.n1b = _f32(blk.norm1.weight), _f32(blk.norm1.bias)
         self.n2w, self.n2b = _f32(blk.norm2.weight), _f32(blk.norm2.bias)
-        self.qkv_w, self.qkv_b = _w_lin(blk.attn.qkv), _f32(blk.attn.qkv.bias)
-        self.proj_w, self.proj_b = _w_lin(blk.attn.proj), _f32(blk.attn.proj.bias)
-        self.fc1_w, self.fc1_b = _w_lin(blk.mlp.fc1), _f32(blk.mlp.fc1.bias)
-        self.fc2_w, self.fc2_b = _w_lin(blk.mlp.fc2), _f32(blk.mlp.fc2.bias)
+        self.qkv_w, self.qkv_b = _w_lin(blk.attn.qkv, x3), _f32(blk.attn.qkv.bias)
+        self.proj_w, self.proj_b = _w_lin(blk.attn.proj, x3), _f32(blk.attn.proj.bias)
+        self.fc1_w, self.fc1_b = _w_lin(blk.mlp.fc1, x3), _f32(blk.mlp.fc1.bias)
+        self.fc2_w, self.fc2_b = _w_lin(blk.mlp.fc2, x3), _f32(blk.mlp.fc2.bias)
 
 
 class _DPTW:
-    def __init__(self, dpt: _DPT):
+    def __init__(self, dpt: _DPT, x3=False):
         ap = dpt.act_postprocess
-        self.ap0 = (_w_lin2d(ap[0][0]), _f32(ap[0][0].bias), _w_convt(ap[0][1]), _f32(ap[0][1].bias))
-        self.ap1 = (_w_lin2d(ap[1][0]), _f32(ap[1][0].bias), _w_convt(ap[1][1]), _f32(ap[1][1].bias))
-        self.ap2 = (_w_lin2d(ap[2][0]), _f32(ap[2][0].bias))
-        w31 = ap[3][1].weight.detach()
-        self.ap3 = (_w_lin2d(ap[3][0]), _f32(ap[3][0].bias),
-                    w31.permute(0, 2, 3, 1).reshape(w31.shape[0], 1, -1).to(BF16).contiguous(), _f32(ap[3][1].bias))
-        self.rn = [_w_conv3(m) for m in dpt.scratch.layer_rn]
+        self.ap0 = (_w_lin2d(ap[0][0], x3), _f32(ap[0][0].bias), _w_convt(ap[0][1], x3), _f32(ap[0][1].bias))
+        self.ap1 = (_w_lin2d(ap[1][0], x3), _f32(ap[1][0].bias), _w_convt(ap[1][1], x3), _f32(ap[1][1].bias))
+        self.ap2 = (_w_lin2d(ap[2][0], x3), _f32(ap[2][0].bias))
+        w31 = _w_conv3(ap[3][1], x3)  # stride-2 conv runs as im2col + linear: (out, 9, C') -> (out, 1, 9*C')
+        self.ap3 = (_w_lin2d(ap[3][0], x3), _f32(ap[3][0].bias), w31.reshape(w31.shape[0], 1, -1), _f32(ap[3][1].bias))
+        self.rn = [_w_conv3(m, x3) for m in dpt.scratch.layer_rn]
         self.fus = {}
         for i in range(1, 5):
             f = getattr(dpt.scratch, f"refinenet{i}")
             self.fus[i] = dict(
-                out_w=_w_lin2d(f.out_conv), out_b=_f32(f.out_conv.bias),
-                r1=(_w_conv3(f.resConfUnit1.conv1), _f32(f.resConfUnit1.conv1.bias),
-                    _w_conv3(f.resConfUnit1.conv2), _f32(f.resConfUnit1.conv2.bias)),
-                r2=(_w_conv3(f.resConfUnit2.conv1), _f32(f.resConfUnit2.conv1.bias),
-                    _w_conv3(f.resConfUnit2.conv2), _f32(f.resConfUnit2.conv2.bias)))
-        self.h0 = (_w_conv3(dpt.head[0]), _f32(dpt.head[0].bias))
-        self.h2 = (_w_conv3(dpt.head[2]), _f32(dpt.head[2].bias))
+                out_w=_w_lin2d(f.out_conv, x3), out_b=_f32(f.out_conv.bias),
+                r1=(_w_conv3(f.resConfUnit1.conv1, x3), _f32(f.resConfUnit1.conv1.bias),
+                    _w_conv3(f.resConfUnit1.conv2, x3), _f32(f.resConfUnit1.conv2.bias)),
+                r2=(_w_conv3(f.resConfUnit2.conv1, x3), _f32(f.resConfUnit2.conv1.bias),
+                    _w_conv3(f.resConfUnit2.conv2, x3), _f32(f.resConfUnit2.conv2.bias)))
+        self.h0 = (_w_conv3(dpt.head[0], x3), _f32(dpt.head[0].bias))
+        self.h2 = (_w_conv3(dpt.head[2], x3), _f32(dpt.head[2].bias))
         self.w4 = dpt.head[4].weight.detach().to(F32).reshape(dpt.head[4].weight.shape[0], -1).contiguous()
         self.b4 = _f32(dpt.head[4].bias)
 
 
-def _w_lin2d(m) -> torch.Tensor:  # 1x1 conv (out,in,1,1) -> (out,1,in)
-    w = m.weight.detach()
-    return w.reshape(w.shape[0], 1, w.shape[1]).to(BF16).contiguous()
+def _sync(device) -> None:
+    """profiling=True synchronises like the reference does (fast3r.py:322-491), on the device of the views."""
+    if device.type == "cuda":
+        torch.cuda.synchronize(device)
 
 
 def _require_cuda(device) -> None:
@@ -238,8 +255,18 @@ def _require_cuda(device) -> None:
 
 
 # --------------------------------------------------------------------------- the model
+PRECISIONS = ("bf16", "fp32")
+
+
 class Fast3R(nn.Module):
-    """Drop-in replacement for fast3r.models.fast3r.Fast3R (same ctor / state_dict / forward contract)."""
+    """Drop-in replacement for fast3r.models.fast3r.Fast3R (same ctor / state_dict / forward contract).
+
+    ``precision`` selects the numeric path of the kernels:
+      * ``"bf16"`` (default, the benchmarked path): bf16 tensor-core operands, fp32 accumulation / residual stream /
+        statistics / outputs - what the reference computes under ``torch.autocast(bfloat16)``, a little closer to fp32.
+      * ``"fp32"`` (parity path): the reference's no-autocast result (``inference(..., dtype="32")``,
+        fast3r/dust3r/inference_multiview.py:41-49) to ~1e-5 rel-L2: activations are stored fp32 and every tensor-core
+        product is evaluated as hi*hi + lo*hi + hi*lo on bf16 pairs (3x the MMA work)."""
 
     def __init__(self, encoder_args: dict, decoder_args: dict, head_args: dict, freeze="none"):
         super().__init__()
@@ -251,15 +278,16 @@ class Fast3R(nn.Module):
         self.build_head(self.head_args)
         self.max_parallel_views_for_head = 25
         self.max_images_per_encoder_chunk = 256
+        self.precision = "bf16"
         # sequence-parallel inference (set by fast3r_b200.parallel.enable_sequence_parallel)
         self.sp_group = None
         # None: per-rank seed offset like the reference (data parallel, fast3r.py:707-708); an int pins the offset
-        # (sequence parallel always uses 0 so that all ranks draw the single-device id stream)
+        # (sequence parallel always broadcasts the rank-0 draw so that all ranks use the single-device id stream)
         self.image_id_rank_offset = None
         self._taps = None  # set to a dict to record per-stage tensors (parity debugging / tests)
         self._host_sink = None  # set by inference(): streams finished head chunks to pinned host memory
-        self._packed = None
-        self._packed_sig = None
+        self._packed = {}
+        self._packed_sig = {}
         self.set_freeze(freeze)
 
     # ---- construction (fast3r/models/fast3r.py:72-157)
@@ -283,9 +311,15 @@ class Fast3R(nn.Module):
         self.depth_mode, self.conf_mode = head_args["depth_mode"], head_args["conf_mode"]
         if not (self.head_type == "dpt" and self.output_mode == "pts3d"):
             raise NotImplementedError(f"unexpected head_type={self.head_type} and output_mode={self.output_mode}")
-        if tuple(self.depth_mode)[0] != "exp" or self.conf_mode is None or tuple(self.conf_mode)[0] != "exp" \
-                or float(self.conf_mode[1]) != 1.0:
-            raise NotImplementedError("fast3r_b200 implements depth_mode=('exp',-inf,inf), conf_mode=('exp',1,inf)")
+        # the fused last-conv epilogue hard-codes postprocess.py:28-64 for depth ('exp', -inf, inf) and conf
+        # ('exp', 1, inf): no clipping.  Anything else would silently differ from the reference, so refuse it.
+        dm, cm = tuple(self.depth_mode), (tuple(self.conf_mode) if self.conf_mode is not None else None)
+        ok = (len(dm) == 3 and dm[0] == "exp" and float(dm[1]) == float("-inf") and float(dm[2]) == float("inf")
+              and cm is not None and len(cm) == 3 and cm[0] == "exp" and float(cm[1]) == 1.0
+              and float(cm[2]) == float("inf"))
+        if not ok:
+            raise NotImplementedError("fast3r_b200 implements depth_mode=('exp',-inf,inf), conf_mode=('exp',1,inf) "
+                                      f"only (got {self.depth_mode}, {self.conf_mode})")
         assert self.decoder_args["depth"] > 9
         l2 = self.decoder_args["depth"]
         ed, dd = self.encoder_args["embed_dim"], self.decoder_args["embed_dim"]
@@ -305,100 +339,127 @@ class Fast3R(nn.Module):
     def set_max_parallel_views_for_head(self, max_parallel_views_for_head):
         self.max_parallel_views_for_head = max_parallel_views_for_head
 
+    def set_precision(self, precision: str):
+        if precision not in PRECISIONS:
+            raise ValueError(f"precision must be one of {PRECISIONS}, got {precision!r}")
+        self.precision = precision
+        return self
+
     def load_state_dict(self, ckpt, **kw):
         r = super().load_state_dict(ckpt, **kw)
-        self._packed = None
+        self._packed, self._packed_sig = {}, {}
         return r
 
     def _tap(self, name, t):
         if self._taps is not None and name not in self._taps:  # first writer wins (global head before local head)
             self._taps[name] = t.detach().float().cpu().clone()
 
-    # ---- packed weights
+    # ---- packed weights (one set per precision, rebuilt when a parameter changes)
     def _signature(self):
         return tuple((p.data_ptr(), p._version) for p in self.parameters())
 
-    def _pack(self, device):
+    def _pack(self, device, x3=False):
+        mode = "fp32" if x3 else "bf16"
         sig = (self._signature(), str(device))
-        if self._packed is not None and self._packed_sig == sig:
-            return self._packed
+        if mode in self._packed and self._packed_sig.get(mode) == sig:
+            return self._packed[mode]
         _require_cuda(device)
+        for name, prm in self.named_parameters():
+            if prm.device != device:
+                raise RuntimeError(f"fast3r_b200: parameter {name} lives on {prm.device} but the views are on {device}; "
+                                   "call model.to(device) first (there is no CPU path)")
         enc, dec = self.encoder, self.decoder
         if enc.embed_dim // enc.num_heads != 64 or dec.embed_dim // dec.num_heads != 64:
             raise NotImplementedError("fast3r_b200 attention kernel is specialised for head_dim 64")
         pe = enc.patch_embed.proj
         P = dict(
-            pe_w=pe.weight.detach().reshape(pe.weight.shape[0], 1, -1).to(BF16).contiguous(), pe_b=_f32(pe.bias),
-            enc=[_BlockW(b) for b in enc.enc_blocks], enc_nw=_f32(enc.enc_norm.weight), enc_nb=_f32(enc.enc_norm.bias),
-            de_w=_w_lin(dec.decoder_embed), de_b=_f32(dec.decoder_embed.bias),
-            dec=[_BlockW(b) for b in dec.dec_blocks], dec_nw=_f32(dec.dec_norm.weight), dec_nb=_f32(dec.dec_norm.bias),
+            pe_w=_pk(pe.weight.detach().reshape(pe.weight.shape[0], 1, -1), x3), pe_b=_f32(pe.bias),
+            enc=[_BlockW(b, x3) for b in enc.enc_blocks], enc_nw=_f32(enc.enc_norm.weight),
+            enc_nb=_f32(enc.enc_norm.bias),
+            de_w=_w_lin(dec.decoder_embed, x3), de_b=_f32(dec.decoder_embed.bias),
+            dec=[_BlockW(b, x3) for b in dec.dec_blocks], dec_nw=_f32(dec.dec_norm.weight),
+            dec_nb=_f32(dec.dec_norm.bias),
             table=dec.image_idx_emb.detach().to(device=device, dtype=F32).contiguous(),
-            head=_DPTW(self.downstream_head.dpt),
-            head_local=_DPTW(self.downstream_head_local.dpt) if self.downstream_head_local is not None else None,
+            head=_DPTW(self.downstream_head.dpt, x3),
+            head_local=_DPTW(self.downstream_head_local.dpt, x3) if self.downstream_head_local is not None else None,
         )
         j = torch.arange(16, dtype=torch.float32)
         ang = torch.arange(256, dtype=torch.float32)[:, None] * (1.0 / (enc.rope_base ** (j / 16.0)))[None]
         P["rope_cos"], P["rope_sin"] = ang.cos().contiguous().to(device), ang.sin().contiguous().to(device)
-        self._packed, self._packed_sig = P, sig
+        self._packed[mode], self._packed_sig[mode] = P, sig
         return P
 
-    # ---- one transformer block (fast3r/croco/models/blocks.py:135-194, 236-239)
+    # ---- GEMM dispatch of the two numeric paths.  ``a`` is a bf16 operand (fast path) or an fp32 activation that is
+    # hi/lo-split on the fly (parity path; ``a_relu`` folds the preceding ReLU into the split).
     @staticmethod
-    def _block(x, w: _BlockW, ws, *, batch, seq, heads, eps, scale, rope=None, kv_exchange=None):
+    def _gemm(x3, a, wt, *, a_relu=False, a_relu_src=None, **kw):
+        if x3:
+            return ops.gemm_x3(a, wt, a_relu=a_relu, **kw)
+        return ops.gemm(a_relu_src if a_relu else a, wt, **kw)
+
+    @classmethod
+    def _linear(cls, x3, a, wt, bias=None, **kw):
+        return cls._gemm(x3, a, wt, w=a.numel() // a.shape[-1], bias=bias, **kw)
+
+    # ---- one transformer block (fast3r/croco/models/blocks.py:135-194, 236-239)
+    @classmethod
+    def _block(cls, x, w: _BlockW, ws, *, batch, seq, heads, eps, scale, rope=None, kv_exchange=None, x3=False):
         M, D = x.shape
         h, q, kv, att, hid = ws["h"][:M], ws["q"][:M], ws["kv"][:M], ws["att"][:M], ws["hid"][:M]
         ops.layernorm(x, w.n1w, w.n1b, eps, h)
         if rope is not None:
-            ops.linear(h, w.qkv_w, w.qkv_b, out0=q, ldo=D, split_col=D, out0b=kv, ldo_b=2 * D, epi=L.EPI_ROPE,
-                       tok_per_img=rope["P"], grid_w=rope["gw"], rope_cols=2 * D, rope_cos=rope["cos"],
-                       rope_sin=rope["sin"])
+            cls._linear(x3, h, w.qkv_w, w.qkv_b, out0=q, ldo=D, split_col=D, out0b=kv, ldo_b=2 * D, epi=L.EPI_ROPE,
+                        tok_per_img=rope["P"], grid_w=rope["gw"], rope_cols=2 * D, rope_cos=rope["cos"],
+                        rope_sin=rope["sin"])
         else:
-            ops.linear(h, w.qkv_w, w.qkv_b, out0=q, ldo=D, split_col=D, out0b=kv, ldo_b=2 * D)
+            cls._linear(x3, h, w.qkv_w, w.qkv_b, out0=q, ldo=D, split_col=D, out0b=kv, ldo_b=2 * D)
+        attn = ops.attention_x3 if x3 else ops.attention
         if kv_exchange is None:
-            ops.attention(q, kv, att, batch=batch, heads=heads, sq=seq, skv=seq, scale=scale)
+            attn(q, kv, att, batch=batch, heads=heads, sq=seq, skv=seq, scale=scale)
         else:
             kv_all, skv = kv_exchange(kv)
-            ops.attention(q, kv_all, att, batch=batch, heads=heads, sq=seq, skv=skv, scale=scale)
-        ops.linear(att, w.proj_w, w.proj_b, out0=x, res0=x)
+            attn(q, kv_all, att, batch=batch, heads=heads, sq=seq, skv=skv, scale=scale)
+        cls._linear(x3, att, w.proj_w, w.proj_b, out0=x, res0=x)
         ops.layernorm(x, w.n2w, w.n2b, eps, h)
-        ops.linear(h, w.fc1_w, w.fc1_b, out0=hid, act=L.ACT_GELU)
-        ops.linear(hid, w.fc2_w, w.fc2_b, out0=x, res0=x)
+        cls._linear(x3, h, w.fc1_w, w.fc1_b, out0=hid, act=L.ACT_GELU)
+        cls._linear(x3, hid, w.fc2_w, w.fc2_b, out0=x, res0=x)
 
     @staticmethod
-    def _workspace(M, D, hidden, device):
-        e = lambda *s: torch.empty(*s, dtype=BF16, device=device)  # noqa: E731
+    def _workspace(M, D, hidden, device, x3=False):
+        e = lambda *s: torch.empty(*s, dtype=F32 if x3 else BF16, device=device)  # noqa: E731
         return dict(h=e(M, D), q=e(M, D), kv=e(M, 2 * D), att=e(M, D), hid=e(M, hidden))
 
     # ---- encoder (fast3r/models/fast3r.py:250-296, 549-559)
-    def _encode(self, imgs: torch.Tensor, P_):
+    def _encode(self, imgs: torch.Tensor, P_, x3=False):
         enc = self.encoder
         n, _, H, W = imgs.shape
         gh, gw = H // enc.patch_size, W // enc.patch_size
         if max(gh, gw) > P_["rope_cos"].shape[0]:
             raise ValueError(f"image too large for the RoPE table ({gh}x{gw} patches > {P_['rope_cos'].shape[0]})")
         P, D = gh * gw, enc.embed_dim
-        feats = torch.empty(n * P, D, dtype=BF16, device=imgs.device)
+        adt = F32 if x3 else BF16
+        feats = torch.empty(n * P, D, dtype=adt, device=imgs.device)
         chunk = self.max_images_per_encoder_chunk
         hidden = enc.enc_blocks[0].mlp.fc1.weight.shape[0]
-        ws = self._workspace(min(n, chunk) * P, D, hidden, imgs.device)
+        ws = self._workspace(min(n, chunk) * P, D, hidden, imgs.device, x3)
         rope = dict(P=P, gw=gw, cos=P_["rope_cos"], sin=P_["rope_sin"])
         for s in range(0, n, chunk):
             c = min(chunk, n - s)
             M = c * P
-            a0 = torch.empty(M, 3 * enc.patch_size * enc.patch_size, dtype=BF16, device=imgs.device)
+            a0 = torch.empty(M, 3 * enc.patch_size * enc.patch_size, dtype=adt, device=imgs.device)
             ops.im2col_patch(imgs[s:s + c], a0)
             x = torch.empty(M, D, dtype=F32, device=imgs.device)
-            ops.linear(a0, P_["pe_w"], P_["pe_b"], out0=x)
+            self._linear(x3, a0, P_["pe_w"], P_["pe_b"], out0=x)
             self._tap("patch_embed", x)
             for li, w in enumerate(P_["enc"]):
-                self._block(x, w, ws, batch=c, seq=P, heads=enc.num_heads, eps=1e-6, scale=64 ** -0.5, rope=rope)
+                self._block(x, w, ws, batch=c, seq=P, heads=enc.num_heads, eps=1e-6, scale=64 ** -0.5, rope=rope, x3=x3)
                 self._tap(f"enc_block{li}", x)
             ops.layernorm(x, P_["enc_nw"], P_["enc_nb"], 1e-6, feats[s * P:(s + c) * P])
         return feats, P, gh, gw
 
     # ---- fusion decoder (fast3r/models/fast3r.py:768-808)
     def _decode(self, feats_bnp: torch.Tensor, ids: torch.Tensor, B: int, n_local: int, P: int, P_, kv_exchange=None,
-                per_token_ids: bool = False):
+                per_token_ids: bool = False, x3=False):
         """feats_bnp: (B*seq, D) tokens in (b, view, patch) order.  ids: (B, n_local) table rows per view (P tokens
         each), or with per_token_ids=True a flat (B*seq,) tensor with one table row per token (mixed resolutions;
         then n_local * P must still equal the per-sample sequence length)."""
@@ -407,71 +468,93 @@ class Fast3R(nn.Module):
         M = feats_bnp.shape[0]
         dev = feats_bnp.device
         x = torch.empty(M, D, dtype=F32, device=dev)
-        ops.linear(feats_bnp, P_["de_w"], P_["de_b"], out0=x, epi=L.EPI_IDXEMB, tok_per_img=0 if per_token_ids else P,
-                   emb_table=P_["table"], emb_ids=ids.to(device=dev, dtype=torch.int32).contiguous())
+        self._linear(x3, feats_bnp, P_["de_w"], P_["de_b"], out0=x, epi=L.EPI_IDXEMB,
+                     tok_per_img=0 if per_token_ids else P, emb_table=P_["table"],
+                     emb_ids=ids.to(device=dev, dtype=torch.int32).contiguous())
         hd = D // dec.num_heads
         if (not self.training) and dec.attn_bias_for_inference_enabled:
             scale = hd ** -0.5 * (1.0 * math.log(137) / math.log(20)) ** 0.5  # blocks.py:119-124
         else:
             scale = hd ** -0.5
         hidden = dec.dec_blocks[0].mlp.fc1.weight.shape[0]
-        ws = self._workspace(M, D, hidden, dev)
+        ws = self._workspace(M, D, hidden, dev, x3)
         depth = dec.depth
         hooks = {depth * 2 // 4: None, depth * 3 // 4: None}
         self._tap("dec_embed", x)
         for i, w in enumerate(P_["dec"]):
             self._block(x, w, ws, batch=B, seq=n_local * P, heads=dec.num_heads, eps=1e-5, scale=scale,
-                        kv_exchange=kv_exchange)
+                        kv_exchange=kv_exchange, x3=x3)
             self._tap(f"dec_block{i}", x)
             if (i + 1) in hooks:
-                t = torch.empty(M, D, dtype=BF16, device=dev)
-                ops.cast_bf16(x, t)
-                hooks[i + 1] = t
-        last = torch.empty(M, D, dtype=BF16, device=dev)
+                if x3:
+                    hooks[i + 1] = x.clone()
+                else:
+                    t = torch.empty(M, D, dtype=BF16, device=dev)
+                    ops.cast_bf16(x, t)
+                    hooks[i + 1] = t
+        last = torch.empty(M, D, dtype=F32 if x3 else BF16, device=dev)
         ops.layernorm(x, P_["dec_nw"], P_["dec_nb"], 1e-6, last)
         return [hooks[depth * 2 // 4], hooks[depth * 3 // 4], last]
 
     # ---- DPT head + postprocess (dpt_head.py:42-90, dpt_block.py, postprocess.py)
-    @staticmethod
-    def _rcu(x, x_relu, w, nv, h, w_, res1=None, want_relu=False):
-        """y = x + conv2(relu(conv1(relu(x)))) (+ res1); returns (y, relu(y) or None)."""
+    @classmethod
+    def _rcu(cls, x, x_relu, w, nv, h, w_, res1=None, want_relu=False, x3=False):
+        """y = x + conv2(relu(conv1(relu(x)))) (+ res1); returns (y, relu(y) or None).  Fast path: relu(x) arrives as
+        the bf16 tensor x_relu and relu(y) is a second epilogue output; parity path: the ReLUs are folded into the
+        operand split of the consuming conv (x_relu / the returned relu(y) are None)."""
         dev = x.device
-        t = torch.empty(nv, h, w_, 256, dtype=BF16, device=dev)
-        ops.gemm(x_relu, w[0], w=w_, h=h, nb=nv, taps=9, bias=w[1], out0=t, act=L.ACT_RELU)
-        y = torch.empty(nv, h, w_, 256, dtype=BF16, device=dev)
+        adt = F32 if x3 else BF16
+        t = torch.empty(nv, h, w_, 256, dtype=adt, device=dev)
+        cls._gemm(x3, x, w[0], a_relu=True, a_relu_src=x_relu, w=w_, h=h, nb=nv, taps=9, bias=w[1], out0=t,
+                  act=L.ACT_RELU)
+        y = torch.empty(nv, h, w_, 256, dtype=adt, device=dev)
+        if x3:
+            ops.gemm_x3(t, w[2], w=w_, h=h, nb=nv, taps=9, bias=w[3], out0=y, res0=x)
+            if res1 is not None:
+                ops.add_f32(y, res1)
+            return y, None
         yr = torch.empty(nv, h, w_, 256, dtype=BF16, device=dev) if want_relu else None
         ops.gemm(t, w[2], w=w_, h=h, nb=nv, taps=9, bias=w[3], out0=y, out1=yr, res0=x, res1=res1)
         return y, yr
 
     def _dpt(self, hooked: List[torch.Tensor], nv: int, gh: int, gw: int, H: int, W: int, hw: _DPTW,
-             pts: torch.Tensor, conf: torch.Tensor):
+             pts: torch.Tensor, conf: torch.Tensor, x3=False):
         dev = hooked[0].device
-        e = lambda *s: torch.empty(*s, dtype=BF16, device=dev)  # noqa: E731
+        adt = F32 if x3 else BF16
+        e = lambda *s: torch.empty(*s, dtype=adt, device=dev)  # noqa: E731
+        g = lambda a, wt, **kw: self._gemm(x3, a, wt, **kw)  # noqa: E731
         # act_postprocess
         a = e(nv, gh, gw, 96)
-        ops.gemm(hooked[0], hw.ap0[0], w=gw, h=gh, nb=nv, bias=hw.ap0[1], out0=a)
+        g(hooked[0], hw.ap0[0], w=gw, h=gh, nb=nv, bias=hw.ap0[1], out0=a)
         l0 = e(nv, 4 * gh, 4 * gw, 96)
-        ops.gemm(a, hw.ap0[2], w=gw, h=gh, nb=nv, bias=hw.ap0[3], out0=l0, epi=L.EPI_CONVT, ct_k=4, ct_cout=96)
+        g(a, hw.ap0[2], w=gw, h=gh, nb=nv, bias=hw.ap0[3], out0=l0, epi=L.EPI_CONVT, ct_k=4, ct_cout=96)
         a = e(nv, gh, gw, 192)
-        ops.gemm(hooked[1], hw.ap1[0], w=gw, h=gh, nb=nv, bias=hw.ap1[1], out0=a)
+        g(hooked[1], hw.ap1[0], w=gw, h=gh, nb=nv, bias=hw.ap1[1], out0=a)
         l1 = e(nv, 2 * gh, 2 * gw, 192)
-        ops.gemm(a, hw.ap1[2], w=gw, h=gh, nb=nv, bias=hw.ap1[3], out0=l1, epi=L.EPI_CONVT, ct_k=2, ct_cout=192)
+        g(a, hw.ap1[2], w=gw, h=gh, nb=nv, bias=hw.ap1[3], out0=l1, epi=L.EPI_CONVT, ct_k=2, ct_cout=192)
         l2 = e(nv, gh, gw, 384)
-        ops.gemm(hooked[2], hw.ap2[0], w=gw, h=gh, nb=nv, bias=hw.ap2[1], out0=l2)
+        g(hooked[2], hw.ap2[0], w=gw, h=gh, nb=nv, bias=hw.ap2[1], out0=l2)
         a = e(nv, gh, gw, 768)
-        ops.gemm(hooked[3], hw.ap3[0], w=gw, h=gh, nb=nv, bias=hw.ap3[1], out0=a)
+        g(hooked[3], hw.ap3[0], w=gw, h=gh, nb=nv, bias=hw.ap3[1], out0=a)
         h3, w3 = (gh + 1) // 2, (gw + 1) // 2
-        col = e(nv * h3 * w3, 9 * 768)
-        ops.im2col3x3s2(a, col, nv, gh, gw, 768, h3, w3)
         l3 = e(nv, h3, w3, 768)
+        if x3:  # stride-2 conv = strided im2col of the split operand (channels [hi | lo | hi]) + linear
+            a3 = torch.empty(nv, gh, gw, 3 * 768, dtype=BF16, device=dev)
+            ops.split3(a, a3)
+            col = torch.empty(nv * h3 * w3, 27 * 768, dtype=BF16, device=dev)
+            ops.im2col3x3s2(a3, col, nv, gh, gw, 3 * 768, h3, w3)
+        else:
+            col = e(nv * h3 * w3, 9 * 768)
+            ops.im2col3x3s2(a, col, nv, gh, gw, 768, h3, w3)
         ops.gemm(col, hw.ap3[2], w=nv * h3 * w3, bias=hw.ap3[3], out0=l3)
         # layer_rn (3x3, no bias): keep x and relu(x)
         dims = [(4 * gh, 4 * gw), (2 * gh, 2 * gw), (gh, gw), (h3, w3)]
         lay, lay_r = [], []
         for i, src in enumerate([l0, l1, l2, l3]):
             hh, ww = dims[i]
-            o, orl = e(nv, hh, ww, 256), e(nv, hh, ww, 256)
-            ops.gemm(src, hw.rn[i], w=ww, h=hh, nb=nv, taps=9, out0=o, out1=orl)
+            o = e(nv, hh, ww, 256)
+            orl = None if x3 else e(nv, hh, ww, 256)
+            g(src, hw.rn[i], w=ww, h=hh, nb=nv, taps=9, out0=o, out1=orl)
             lay.append(o)
             lay_r.append(orl)
             self._tap(f"layer_rn{i}", o)
@@ -479,30 +562,57 @@ class Fast3R(nn.Module):
         def out_conv_up(y, f, hh, ww, ho, wo):
             # 1x1 out_conv commutes with the bilinear upsample (weights sum to 1): do it at low resolution
             z = e(nv, hh, ww, 256)
-            ops.gemm(y, f["out_w"], w=ww, h=hh, nb=nv, bias=f["out_b"], out0=z)
+            g(y, f["out_w"], w=ww, h=hh, nb=nv, bias=f["out_b"], out0=z)
             up = e(nv, ho, wo, 256)
             ops.upsample2x(z, up, nv, hh, ww, 256, ho, wo)
             return up
 
         # refinenet4 (single input; output cropped to layer-3 size, dpt_head.py:69-71)
-        y, _ = self._rcu(lay[3], lay_r[3], hw.fus[4]["r2"], nv, h3, w3)
+        y, _ = self._rcu(lay[3], lay_r[3], hw.fus[4]["r2"], nv, h3, w3, x3=x3)
         path = out_conv_up(y, hw.fus[4], h3, w3, gh, gw)
         self._tap("path4", path)
         for lvl, i in ((3, 2), (2, 1), (1, 0)):
             hh, ww = dims[i]
             f = hw.fus[lvl]
-            s, sr = self._rcu(lay[i], lay_r[i], f["r1"], nv, hh, ww, res1=path, want_relu=True)  # path + RCU1(layer)
-            y, _ = self._rcu(s, sr, f["r2"], nv, hh, ww)
+            s, sr = self._rcu(lay[i], lay_r[i], f["r1"], nv, hh, ww, res1=path, want_relu=True, x3=x3)
+            y, _ = self._rcu(s, sr, f["r2"], nv, hh, ww, x3=x3)
             path = out_conv_up(y, f, hh, ww, 2 * hh, 2 * ww)
             self._tap(f"path{lvl}", path)
         # head: conv3x3 256->128, x2 bilinear, conv3x3 128->128 + ReLU + conv1x1 128->4 + postprocess (fused)
         hh, ww = 8 * gh, 8 * gw
         t = e(nv, hh, ww, 128)
-        ops.gemm(path, hw.h0[0], w=ww, h=hh, nb=nv, taps=9, bias=hw.h0[1], out0=t)
+        g(path, hw.h0[0], w=ww, h=hh, nb=nv, taps=9, bias=hw.h0[1], out0=t)
         up = e(nv, H, W, 128)
         ops.upsample2x(t, up, nv, hh, ww, 128, H, W)
-        ops.gemm(up, hw.h2[0], w=W, h=H, nb=nv, taps=9, bias=hw.h2[1], epi=L.EPI_FINAL, w4=hw.w4, b4=hw.b4,
-                 pts=pts, conf=conf)
+        g(up, hw.h2[0], w=W, h=H, nb=nv, taps=9, bias=hw.h2[1], epi=L.EPI_FINAL, w4=hw.w4, b4=hw.b4, pts=pts, conf=conf)
+
+    def _run_heads(self, hooked, nvt, P, gh, gw, H, W, P_, device, x3):
+        """All views of one resolution through the global (and local) DPT head in chunks of
+        max_parallel_views_for_head (fast3r.py:430-444).  Returns {"pts", "conf"[, "pts_local", "conf_local"]}."""
+        heads = [("", P_["head"])] + ([("_local", P_["head_local"])] if P_["head_local"] is not None else [])
+        outs = {}
+        for suffix, _hw in heads:
+            outs["pts" + suffix] = torch.empty(nvt, H, W, 3, dtype=F32, device=device)
+            outs["conf" + suffix] = torch.empty(nvt, H, W, dtype=F32, device=device)
+        step = max(1, int(self.max_parallel_views_for_head))
+        if x3:
+            step = min(step, 8)  # fp32 feature maps + split scratch are ~5x the bf16 footprint
+        for s in range(0, nvt, step):
+            c = min(step, nvt - s)
+            hk = [t[s * P:(s + c) * P] for t in hooked]
+            for suffix, hw in heads:
+                self._dpt(hk, c, gh, gw, H, W, hw, outs["pts" + suffix][s:s + c], outs["conf" + suffix][s:s + c], x3=x3)
+            if self._host_sink is not None:  # D2H of this chunk overlaps the heads of the next one (SURVEY §8 f1)
+                self._host_sink.chunk_done(list(outs.values()), s, c)
+        return outs
+
+    @staticmethod
+    def _fill_result(r, outs, j, B):
+        r["pts3d_in_other_view"] = outs["pts"][j * B:(j + 1) * B]
+        r["conf"] = outs["conf"][j * B:(j + 1) * B]
+        if "pts_local" in outs:
+            r["pts3d_local"] = outs["pts_local"][j * B:(j + 1) * B]
+            r["conf_local"] = outs["conf_local"][j * B:(j + 1) * B]
 
     # ---- views of different resolutions (fast3r/models/fast3r.py:276-294, 364-376, 407-428)
     def _forward_mixed(self, views, profiling=False):
@@ -514,7 +624,8 @@ class Fast3R(nn.Module):
         profiling_info = {} if profiling else None
         t_start = time.time()
         device = views[0]["img"].device
-        P_ = self._pack(device)
+        x3 = self.precision == "fp32"
+        P_ = self._pack(device, x3)
         N = len(views)
         B = views[0]["img"].shape[0]
         ps = self.encoder.patch_size
@@ -531,12 +642,12 @@ class Fast3R(nn.Module):
         genc = {}
         for (H, W), idxs in groups.items():
             imgs = torch.cat([views[i]["img"] for i in idxs], dim=0).to(dtype=F32).contiguous()
-            feats, P, gh, gw = self._encode(imgs, P_)  # ((n_g*B)*P, D) in (n, b, p) order
+            feats, P, gh, gw = self._encode(imgs, P_, x3)  # ((n_g*B)*P, D) in (n, b, p) order
             genc[(H, W)] = (feats, P, gh, gw)
             for i in idxs:
                 tok[i] = P
         if profiling:
-            torch.cuda.synchronize()
+            _sync(device)
             profiling_info["encode_images_time"] = time.time() - t_start
         t1 = time.time()
         ids = self.decoder.draw_image_ids(B, N, rank_offset=self.image_id_rank_offset)
@@ -546,60 +657,38 @@ class Fast3R(nn.Module):
         S = off[-1]
         if profiling:
             profiling_info["pos_emb_time"] = time.time() - t1
-            torch.cuda.synchronize()
+            _sync(device)
         t2 = time.time()
-        # scatter the per-group encoder outputs into (b, view, patch) order
-        feats_bnp = torch.empty(B * S, D, dtype=BF16, device=device)
+        # (b, view, patch) row of every encoder token: one index_copy per resolution group instead of per-view slices
+        adt = F32 if x3 else BF16
+        feats_bnp = torch.empty(B * S, D, dtype=adt, device=device)
         tok_ids = torch.empty(B, S, dtype=torch.int32)
+        rows = {}
         for (H, W), idxs in groups.items():
             feats, P, _, _ = genc[(H, W)]
-            fv = feats.view(len(idxs), B, P, D)
-            for k, i in enumerate(idxs):
-                for b in range(B):
-                    feats_bnp[b * S + off[i]: b * S + off[i] + P] = fv[k, b]
-                    tok_ids[b, off[i]: off[i] + P] = int(ids[b, i])
-        h12, h18, h24 = self._decode(feats_bnp, tok_ids.reshape(-1), B, 1, S, P_, per_token_ids=True)
+            base = torch.tensor([off[i] for i in idxs], dtype=torch.long)  # (n_g,)
+            r = (base[:, None, None] + torch.arange(B, dtype=torch.long)[None, :, None] * S
+                 + torch.arange(P, dtype=torch.long)[None, None, :]).reshape(-1).to(device)  # (n_g, B, P) order
+            rows[(H, W)] = r
+            feats_bnp.index_copy_(0, r, feats)
+            for i in idxs:
+                tok_ids[:, off[i]: off[i] + P] = ids[:, i:i + 1].to(torch.int32)
+        h12, h18, h24 = self._decode(feats_bnp, tok_ids.reshape(-1), B, 1, S, P_, per_token_ids=True, x3=x3)
         if profiling:
-            torch.cuda.synchronize()
+            _sync(device)
             profiling_info["decoder_time"] = time.time() - t2
         t3 = time.time()
-        Dd = self.decoder.embed_dim
-        heads = [("", P_["head"])] + ([("_local", P_["head_local"])] if P_["head_local"] is not None else [])
         final_results = [{} for _ in range(N)]
         t4 = time.time()
         for (H, W), idxs in groups.items():
             feats, P, gh, gw = genc[(H, W)]
-            ng = len(idxs)
-
-            def regroup(t):  # (b, view, patch) -> '(n b) p' for this group's views
-                o = torch.empty(ng * B * P, Dd, dtype=BF16, device=device)
-                ov = o.view(ng, B, P, Dd)
-                for k, i in enumerate(idxs):
-                    for b in range(B):
-                        ov[k, b] = t[b * S + off[i]: b * S + off[i] + P]
-                return o
-
-            hooked = [feats, regroup(h12), regroup(h18), regroup(h24)]
-            nvt = ng * B
-            outs = {}
-            for suffix, _hw in heads:
-                outs["pts" + suffix] = torch.empty(nvt, H, W, 3, dtype=F32, device=device)
-                outs["conf" + suffix] = torch.empty(nvt, H, W, dtype=F32, device=device)
-            step = max(1, int(self.max_parallel_views_for_head))
-            for s in range(0, nvt, step):
-                c = min(step, nvt - s)
-                hk = [t[s * P:(s + c) * P] for t in hooked]
-                for suffix, hw in heads:
-                    self._dpt(hk, c, gh, gw, H, W, hw, outs["pts" + suffix][s:s + c], outs["conf" + suffix][s:s + c])
+            r = rows[(H, W)]
+            hooked = [feats, h12.index_select(0, r), h18.index_select(0, r), h24.index_select(0, r)]  # '(n b) p'
+            outs = self._run_heads(hooked, len(idxs) * B, P, gh, gw, H, W, P_, device, x3)
             for k, i in enumerate(idxs):
-                r = final_results[i]
-                r["pts3d_in_other_view"] = outs["pts"][k * B:(k + 1) * B]
-                r["conf"] = outs["conf"][k * B:(k + 1) * B]
-                if "pts_local" in outs:
-                    r["pts3d_local"] = outs["pts_local"][k * B:(k + 1) * B]
-                    r["conf_local"] = outs["conf_local"][k * B:(k + 1) * B]
+                self._fill_result(final_results[i], outs, k, B)
         if profiling:
-            torch.cuda.synchronize()
+            _sync(device)
             t_end = time.time()
             profiling_info["head_prepare_input_time"] = t4 - t3
             profiling_info["head_forward_time"] = t_end - t4
@@ -613,6 +702,8 @@ class Fast3R(nn.Module):
             raise NotImplementedError(
                 "fast3r_b200.Fast3R has no backward kernels (training step, SURVEY a13 / config 5, is not built): "
                 "call it under torch.no_grad() for a forward-only pass, or use model.eval()")
+        if self.precision not in PRECISIONS:
+            raise ValueError(f"precision must be one of {PRECISIONS}, got {self.precision!r}")
         with torch.no_grad():
             return self._forward(views, profiling)
 
@@ -627,7 +718,8 @@ class Fast3R(nn.Module):
         device = views[0]["img"].device
         if self.sp_group is not None and device.type != "cuda":
             device = next(self.parameters()).device  # sharded forward: host views are uploaded per rank below
-        P_ = self._pack(device)
+        x3 = self.precision == "fp32"
+        P_ = self._pack(device, x3)
         N = len(views)
         B, _, H, W = views[0]["img"].shape
         ps = self.encoder.patch_size
@@ -649,16 +741,20 @@ class Fast3R(nn.Module):
         imgs = torch.cat([views[i]["img"].to(device, non_blocking=True) for i in range(lo, hi)],
                          dim=0).to(dtype=F32).contiguous()  # (n_loc*B, 3, H, W)
 
-        feats, P, gh, gw = self._encode(imgs, P_)  # (n_loc*B*P, D), order (n, b, p)
+        feats, P, gh, gw = self._encode(imgs, P_, x3)  # (n_loc*B*P, D), order (n, b, p)
         if profiling:
-            torch.cuda.synchronize()
+            _sync(device)
             profiling_info["encode_images_time"] = time.time() - t_start
         t1 = time.time()
-        # image ids: same host RNG stream as the reference (all sequence-parallel ranks draw the rank-0 stream)
+        # image ids: same host RNG stream as the reference.  Sequence parallel: every rank consumes its own RNG draw
+        # (same side effect as the reference) but uses the ids rank 0 drew, so the result equals the single-device
+        # forward whatever the per-rank RNG states are.
         ids = self.decoder.draw_image_ids(B, N, rank_offset=0 if sp is not None else self.image_id_rank_offset)
+        if sp is not None:
+            ids = sp.broadcast_ids(ids, device)
         if profiling:
             profiling_info["pos_emb_time"] = time.time() - t1
-            torch.cuda.synchronize()
+            _sync(device)
         t2 = time.time()
         D = self.encoder.embed_dim
         if B == 1:
@@ -667,9 +763,9 @@ class Fast3R(nn.Module):
             feats_bnp = feats.view(n_loc, B, P, D).permute(1, 0, 2, 3).contiguous().view(-1, D)
         ids_loc = ids[:, lo:hi].contiguous()
         kvx = sp.make_kv_exchange(B, n_loc * P, self.decoder.embed_dim) if sp is not None else None
-        h12, h18, h24 = self._decode(feats_bnp, ids_loc, B, n_loc, P, P_, kv_exchange=kvx)
+        h12, h18, h24 = self._decode(feats_bnp, ids_loc, B, n_loc, P, P_, kv_exchange=kvx, x3=x3)
         if profiling:
-            torch.cuda.synchronize()
+            _sync(device)
             profiling_info["decoder_time"] = time.time() - t2
         t3 = time.time()
         Dd = self.decoder.embed_dim
@@ -681,33 +777,14 @@ class Fast3R(nn.Module):
         if profiling:
             profiling_info["head_prepare_input_time"] = time.time() - t3
         t4 = time.time()
-        nvt = n_loc * B
-        outs = {}
-        heads = [("", P_["head"])] + ([("_local", P_["head_local"])] if P_["head_local"] is not None else [])
-        for suffix, _hw in heads:
-            outs["pts" + suffix] = torch.empty(nvt, H, W, 3, dtype=F32, device=device)
-            outs["conf" + suffix] = torch.empty(nvt, H, W, dtype=F32, device=device)
-        step = max(1, int(self.max_parallel_views_for_head))
-        for s in range(0, nvt, step):
-            c = min(step, nvt - s)
-            hk = [t[s * P:(s + c) * P] for t in hooked]
-            for suffix, hw in heads:
-                self._dpt(hk, c, gh, gw, H, W, hw, outs["pts" + suffix][s:s + c], outs["conf" + suffix][s:s + c])
-            if self._host_sink is not None:  # D2H of this chunk overlaps the heads of the next one
-                self._host_sink.chunk_done(list(outs.values()), s, c)
+        outs = self._run_heads(hooked, n_loc * B, P, gh, gw, H, W, P_, device, x3)
         final_results = [{} for _ in range(N)]
         for i in range(lo, hi):
-            j = i - lo
-            r = final_results[i]
-            r["pts3d_in_other_view"] = outs["pts"][j * B:(j + 1) * B]
-            r["conf"] = outs["conf"][j * B:(j + 1) * B]
-            if "pts_local" in outs:
-                r["pts3d_local"] = outs["pts_local"][j * B:(j + 1) * B]
-                r["conf_local"] = outs["conf_local"][j * B:(j + 1) * B]
+            self._fill_result(final_results[i], outs, i - lo, B)
         if sp is not None and sp.gather_preds:
             final_results = sp.gather_results(final_results, N, B, H, W, device)
         if profiling:
-            torch.cuda.synchronize()
+            _sync(device)
             t_end = time.time()
             profiling_info["head_forward_time"] = t_end - t4
             profiling_info["total_time"] = t_end - t_start

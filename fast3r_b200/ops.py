@@ -17,8 +17,27 @@ BF16, F32 = torch.bfloat16, torch.float32
 KERNEL_TIMER = None
 
 
-def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+def _stream(t: Optional[torch.Tensor] = None) -> int:
+    """The current stream OF THE TENSOR'S DEVICE (callers need not have made that device current)."""
+    return torch.cuda.current_stream(t.device if t is not None else None).cuda_stream
+
+
+class _on_device:
+    """CUDA runtime calls inside the library (cudaFuncSetAttribute, launches) act on the CURRENT device: make the
+    operand's device current for the duration of the call."""
+
+    def __init__(self, t: torch.Tensor):
+        self.idx = t.device.index if t.is_cuda else None
+
+    def __enter__(self):
+        self.prev = None
+        if self.idx is not None and torch.cuda.current_device() != self.idx:
+            self.prev = torch.cuda.current_device()
+            torch.cuda.set_device(self.idx)
+
+    def __exit__(self, *exc):
+        if self.prev is not None:
+            torch.cuda.set_device(self.prev)
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -82,7 +101,34 @@ def gemm(a: torch.Tensor, wt: torch.Tensor, *, w: int, h: int = 1, nb: int = 1, 
     d.rope_cos, d.rope_sin = _ptr(rope_cos), _ptr(rope_sin)
     d.emb_table, d.emb_ids = _ptr(emb_table), _ptr(emb_ids)
     d.w4, d.b4, d.pts, d.conf = _ptr(w4), _ptr(b4), _ptr(pts), _ptr(conf)
-    L.check(L.load().f3r_gemm(C.byref(d), _stream()), "f3r_gemm")
+    with _on_device(a):
+        L.check(L.load().f3r_gemm(C.byref(d), _stream(a)), "f3r_gemm")
+
+
+def gemm_x3(a: torch.Tensor, wt3: torch.Tensor, *, a_relu: bool = False, **kw):
+    """Parity-mode GEMM: a fp32 (..., K) is split into bf16 [hi | lo | hi] (optionally of relu(a)) and multiplied with
+    wt3 = bf16 (N, taps, 3K) packed as [Whi | Whi | Wlo]: hi*hi + lo*hi + hi*lo accumulated in fp32."""
+    _chk(a, F32, "a")
+    k = a.shape[-1]
+    assert wt3.shape[-1] == 3 * k, (wt3.shape, k)
+    a3 = torch.empty(a.shape[:-1] + (3 * k,), dtype=BF16, device=a.device)
+    split3(a, a3, relu=a_relu)
+    return gemm(a3, wt3, **kw)
+
+
+def split3(x: torch.Tensor, out: torch.Tensor, relu: bool = False):
+    _chk(x, F32, "x"); _chk(out, BF16, "out")
+    k = x.shape[-1]
+    assert out.numel() == 3 * x.numel()
+    with _on_device(x):
+        L.check(L.load().f3r_split3(_ptr(x), _ptr(out), x.numel() // k, k, int(relu), _stream(x)), "f3r_split3")
+
+
+def add_f32(dst: torch.Tensor, src: torch.Tensor):
+    _chk(dst, F32, "dst"); _chk(src, F32, "src")
+    assert dst.numel() == src.numel()
+    with _on_device(dst):
+        L.check(L.load().f3r_add_f32(_ptr(dst), _ptr(src), dst.numel(), _stream(dst)), "f3r_add_f32")
 
 
 def linear(a: torch.Tensor, wt: torch.Tensor, bias=None, **kw):
@@ -97,44 +143,68 @@ def attention(q: torch.Tensor, kv: torch.Tensor, out: torch.Tensor, *, batch: in
     ldq, ldkv, ldo = q.shape[-1], kv.shape[-1], out.shape[-1]
     assert q.numel() == batch * sq * ldq and kv.numel() == batch * skv * ldkv and out.numel() == batch * sq * ldo
     timer = KERNEL_TIMER
+    st = torch.cuda.current_stream(q.device)
     if timer is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-    L.check(L.load().f3r_attention(_ptr(q), ldq, _ptr(kv), ldkv, _ptr(out), ldo, _ptr(lse), batch, heads, sq, skv,
-                                   float(scale), _stream()), "f3r_attention")
+        e0.record(st)
+    with _on_device(q):
+        L.check(L.load().f3r_attention(_ptr(q), ldq, _ptr(kv), ldkv, _ptr(out), ldo, _ptr(lse), batch, heads, sq, skv,
+                                       float(scale), st.cuda_stream), "f3r_attention")
     if timer is not None:
-        e1.record()
+        e1.record(st)
         timer.append((batch, heads, sq, skv, e0, e1))
+
+
+def attention_x3(q: torch.Tensor, kv: torch.Tensor, out: torch.Tensor, *, batch: int, heads: int, sq: int, skv: int,
+                 scale: float, lse: Optional[torch.Tensor] = None):
+    """Parity-mode attention: q (batch*sq, ldq), kv (batch*skv, ldkv) [K | V], out (batch*sq, ldo), all fp32."""
+    _chk(q, F32, "q"); _chk(kv, F32, "kv"); _chk(out, F32, "out")
+    ldq, ldkv, ldo = q.shape[-1], kv.shape[-1], out.shape[-1]
+    assert q.numel() == batch * sq * ldq and kv.numel() == batch * skv * ldkv and out.numel() == batch * sq * ldo
+    lib = L.load()
+    nbytes = int(lib.f3r_attention_x3_workspace(batch, heads, sq, skv))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=q.device)  # caching allocator: >= 512-byte aligned
+    with _on_device(q):
+        L.check(lib.f3r_attention_x3(_ptr(q), ldq, _ptr(kv), ldkv, _ptr(out), ldo, _ptr(lse), _ptr(ws), nbytes, batch,
+                                     heads, sq, skv, float(scale), _stream(q)), "f3r_attention_x3")
 
 
 def layernorm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float, out: torch.Tensor):
     _chk(x, F32, "x"); _chk(w, F32, "w"); _chk(b, F32, "b")
     assert out.dtype in (BF16, F32) and out.is_contiguous() and out.numel() == x.numel()
     dim = x.shape[-1]
-    L.check(L.load().f3r_layernorm(_ptr(x), _ptr(w), _ptr(b), _ptr(out), int(out.dtype == F32), x.numel() // dim,
-                                   dim, float(eps), _stream()), "f3r_layernorm")
+    with _on_device(x):
+        L.check(L.load().f3r_layernorm(_ptr(x), _ptr(w), _ptr(b), _ptr(out), int(out.dtype == F32), x.numel() // dim,
+                                       dim, float(eps), _stream(x)), "f3r_layernorm")
 
 
 def im2col_patch(img: torch.Tensor, out: torch.Tensor):
-    _chk(img, F32, "img"); _chk(out, BF16, "out")
+    _chk(img, F32, "img")
+    assert out.dtype in (BF16, F32) and out.is_contiguous()
     n, c, h, w = img.shape
     assert c == 3 and out.numel() == n * (h // 16) * (w // 16) * 768
-    L.check(L.load().f3r_im2col_patch(_ptr(img), _ptr(out), n, h, w, _stream()), "f3r_im2col_patch")
+    with _on_device(img):
+        L.check(L.load().f3r_im2col_patch(_ptr(img), _ptr(out), int(out.dtype == F32), n, h, w, _stream(img)),
+                "f3r_im2col_patch")
 
 
 def im2col3x3s2(x: torch.Tensor, out: torch.Tensor, n: int, h: int, w: int, c: int, ho: int, wo: int):
     _chk(x, BF16, "x"); _chk(out, BF16, "out")
     assert x.numel() == n * h * w * c and out.numel() == n * ho * wo * 9 * c
-    L.check(L.load().f3r_im2col3x3s2(_ptr(x), _ptr(out), n, h, w, c, ho, wo, _stream()), "f3r_im2col3x3s2")
+    with _on_device(x):
+        L.check(L.load().f3r_im2col3x3s2(_ptr(x), _ptr(out), n, h, w, c, ho, wo, _stream(x)), "f3r_im2col3x3s2")
 
 
 def upsample2x(x: torch.Tensor, out: torch.Tensor, n: int, h: int, w: int, c: int, ho: int, wo: int):
-    _chk(x, BF16, "x"); _chk(out, BF16, "out")
+    assert x.dtype in (BF16, F32) and x.dtype == out.dtype and x.is_contiguous() and out.is_contiguous()
     assert x.numel() == n * h * w * c and out.numel() == n * ho * wo * c
-    L.check(L.load().f3r_upsample2x(_ptr(x), _ptr(out), n, h, w, c, ho, wo, _stream()), "f3r_upsample2x")
+    with _on_device(x):
+        L.check(L.load().f3r_upsample2x(_ptr(x), _ptr(out), int(x.dtype == F32), n, h, w, c, ho, wo, _stream(x)),
+                "f3r_upsample2x")
 
 
 def cast_bf16(x: torch.Tensor, out: torch.Tensor):
     _chk(x, F32, "x"); _chk(out, BF16, "out")
     assert x.numel() == out.numel()
-    L.check(L.load().f3r_cast_bf16(_ptr(x), _ptr(out), x.numel(), _stream()), "f3r_cast_bf16")
+    with _on_device(x):
+        L.check(L.load().f3r_cast_bf16(_ptr(x), _ptr(out), x.numel(), _stream(x)), "f3r_cast_bf16")

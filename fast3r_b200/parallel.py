@@ -4,8 +4,8 @@ The reference has no counterpart (no TP/PP/SP anywhere); the sin
 Partitioning: rank r owns a contiguous range of views, i.e. a contiguous token range of the
 N*P-token sequence.  Encoder blocks, LayerNorm, all linears and the DPT heads are token/view-local and need no
 communication; only the global attention couples ranks: each decoder layer all-gathers K|V (bf16, S_local x 2D)
-over NCCL/NVLink and every rank attends its local queries against all keys.  All ranks draw the image-index ids
-from the rank-0 RNG stream so the result equals the single-device forward.
+over NCCL/NVLink and every rank attends its local queries against all keys.  The image-index ids drawn by rank 0 are
+broadcast to all ranks so the result equals the single-device forward whatever the per-rank RNG states are.
 """
 from __future__ import annotations
 
@@ -54,6 +54,17 @@ class SequenceParallel:
         if any(hi - lo == 0 for lo, hi in self._ranges):
             raise ValueError(f"sequence parallel needs at least one view per rank ({num_views} views, {self.world} ranks)")
         return self._ranges[self.rank]
+
+    def broadcast_ids(self, ids: torch.Tensor, device) -> torch.Tensor:
+        """Every rank uses the image ids drawn by rank 0 of the group (the single-device stream), whatever its own CPU
+        RNG state is; each rank has still consumed its own draw, like the reference does per forward."""
+        if self.world == 1:
+            return ids
+        src = dist.get_global_rank(self.group, 0) if self.group is not None else 0
+        on_gpu = dist.get_backend(self.group) == "nccl"
+        t = ids.to(device) if on_gpu else ids.clone()
+        dist.broadcast(t, src=src, group=self.group)
+        return t.cpu()
 
     def make_kv_exchange(self, batch: int, s_local: int, dim: int):
         """Returns kv_exchange(kv_local (batch*s_local, 2*dim) bf16) -> (kv_all (batch*s_total, 2*dim), s_total)."""

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define F3R_ABI_VERSION 1
+#define F3R_ABI_VERSION 2
 
 /* epilogue kinds of f3r_gemm */
 enum { F3R_EPI_STORE = 0, F3R_EPI_ROPE = 1, F3R_EPI_IDXEMB = 2, F3R_EPI_CONVT = 3, F3R_EPI_FINAL = 4 };
@@ -87,17 +87,35 @@ int f3r_attention(const void* q, int32_t ldq, const void* kv, int32_t ldkv, void
 /* nn.LayerNorm over the last dim of fp32 x [rows, dim] -> bf16 (or fp32) out  (blocks.py:219,228; fast3r.py:558,805) */
 int f3r_layernorm(const float* x, const float* w, const float* b, void* out, int32_t out_f32, int32_t rows,
                   int32_t dim, float eps, void* stream);
-/* fp32 image batch (n,3,H,W) -> bf16 [n*(H/16)*(W/16), 768] patch rows (im2col of blocks.py:412 Conv2d k=s=16) */
-int f3r_im2col_patch(const float* img, void* out, int32_t n, int32_t h, int32_t w, void* stream);
+/* fp32 image batch (n,3,H,W) -> bf16 (or, out_f32 != 0, fp32) [n*(H/16)*(W/16), 768] patch rows
+ * (im2col of blocks.py:412 Conv2d k=s=16) */
+int f3r_im2col_patch(const float* img, void* out, int32_t out_f32, int32_t n, int32_t h, int32_t w, void* stream);
 /* bf16 NHWC (n,h,w,c) -> bf16 [n*ho*wo, 9*c] for the 3x3 stride-2 pad-1 conv (dpt_block.py:471-478) */
 int f3r_im2col3x3s2(const void* in, void* out, int32_t n, int32_t h, int32_t w, int32_t c, int32_t ho, int32_t wo,
                     void* stream);
-/* bilinear x2 align_corners=True on bf16 NHWC; writes the top-left (ho, wo) window of the (2h, 2w) result
- * (dpt_block.py:234-247,374; crop of dpt_head.py:69-71) */
-int f3r_upsample2x(const void* in, void* out, int32_t n, int32_t h, int32_t w, int32_t c, int32_t ho, int32_t wo,
-                   void* stream);
+/* bilinear x2 align_corners=True on bf16 (f32 != 0: fp32) NHWC; writes the top-left (ho, wo) window of the (2h, 2w)
+ * result (dpt_block.py:234-247,374; crop of dpt_head.py:69-71) */
+int f3r_upsample2x(const void* in, void* out, int32_t f32, int32_t n, int32_t h, int32_t w, int32_t c, int32_t ho,
+                   int32_t wo, void* stream);
 /* fp32 -> bf16, count multiple of 4 */
 int f3r_cast_bf16(const float* in, void* out, size_t count, void* stream);
+
+
+/* ---- parity mode: the reference's fp32 path (inference_multiview.py:41-49, dtype="32": no autocast) on the bf16
+ * tensor pipe.  Every fp32 operand x is carried as hi + lo (two bf16), every product as hi*hi + lo*hi + hi*lo with
+ * fp32 accumulation.  For f3r_gemm this is the ordinary kernel over a 3x longer K: A' = f3r_split3(A) = [hi|lo|hi],
+ * weights packed by the caller as [Whi | Whi | Wlo] along K (per tap); all outputs fp32 (out0_f32). */
+
+/* fp32 in [rows, k] -> bf16 out [rows, 3k] = [hi | lo | hi] of x (relu != 0: of max(x, 0)) */
+int f3r_split3(const float* in, void* out, size_t rows, int32_t k, int32_t relu, void* stream);
+/* dst[i] += src[i], fp32, count multiple of 4 (second residual operand of dpt_block.py:241 in parity mode) */
+int f3r_add_f32(float* dst, const float* src, size_t count, void* stream);
+/* Same contract as f3r_attention with fp32 q / kv / out (blocks.py:135-194 without autocast).  workspace: caller-owned
+ * device scratch of at least f3r_attention_x3_workspace() bytes, 256-byte aligned (holds the split operands). */
+size_t f3r_attention_x3_workspace(int32_t batch, int32_t heads, int32_t sq, int32_t skv);
+int f3r_attention_x3(const float* q, int32_t ldq, const float* kv, int32_t ldkv, float* out, int32_t ldo, float* lse,
+                     void* workspace, size_t workspace_bytes, int32_t batch, int32_t heads, int32_t sq, int32_t skv,
+                     float scale, void* stream);
 
 #ifdef __cplusplus
 }

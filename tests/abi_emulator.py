@@ -84,6 +84,45 @@ def linear(a, wt, bias=None, **kw):
     return gemm(a, wt, w=a.numel() // a.shape[-1], bias=bias, **kw)
 
 
+def _hi_lo(x):
+    hi = x.float().to(BF16)
+    return hi, (x.float() - hi.float()).to(BF16)
+
+
+def split3(x, out, relu=False):
+    v = F.relu(x.float()) if relu else x.float()
+    hi, lo = _hi_lo(v)
+    _store(out, torch.cat([hi, lo, hi], dim=-1))
+
+
+def gemm_x3(a, wt3, *, a_relu=False, **kw):
+    a3 = torch.empty(a.shape[:-1] + (3 * a.shape[-1],), dtype=BF16)
+    split3(a, a3, relu=a_relu)
+    return gemm(a3, wt3, **kw)
+
+
+def add_f32(dst, src):
+    dst.add_(src.reshape(dst.shape))
+
+
+def attention_x3(q, kv, out, *, batch, heads, sq, skv, scale, lse=None):
+    """hi/lo-split operands, products hi*hi + lo*hi + hi*lo, fp32 softmax, fp32 output."""
+    D = heads * 64
+    qh = q.reshape(batch, sq, heads, 64).transpose(1, 2)
+    kh = kv[:, :D].reshape(batch, skv, heads, 64).transpose(1, 2)
+    vh = kv[:, D:].reshape(batch, skv, heads, 64).transpose(1, 2)
+    (q_hi, q_lo), (k_hi, k_lo), (v_hi, v_lo) = _hi_lo(qh), _hi_lo(kh), _hi_lo(vh)
+    kt_hi, kt_lo = k_hi.float().transpose(-2, -1), k_lo.float().transpose(-2, -1)
+    s = (q_hi.float() @ kt_hi + q_lo.float() @ kt_hi + q_hi.float() @ kt_lo) * scale
+    m = s.amax(-1, keepdim=True)
+    p = torch.exp(s - m)
+    p_hi, p_lo = _hi_lo(p)
+    o = (p_hi.float() @ v_hi.float() + p_lo.float() @ v_hi.float() + p_hi.float() @ v_lo.float()) / p.sum(-1, keepdim=True)
+    _store(out, o.transpose(1, 2).reshape(batch * sq, D))
+    if lse is not None:
+        _store(lse, torch.logsumexp(s, -1))
+
+
 def attention(q, kv, out, *, batch, heads, sq, skv, scale, lse=None):
     D = heads * 64
     qh = q.reshape(batch, sq, heads, 64).transpose(1, 2).float()

@@ -154,7 +154,47 @@ def run_blocks():
     print("vitl_blocks saved", os.path.getsize(os.path.join(HERE, "vitl_blocks.pt")) / 1e6, "MB")
 
 
+def run_vitl_n4(tag="vitl_n4_368x512", stride=4):
+    """BASELINE.json configs[0]: full ViT-L/512 (24+24 layers, 2 DPT heads), N=4 views 512x368, fp32 on CPU through the
+    reference's own inference(..., dtype="32").  The full-resolution preds are 24 MB, so the fixture keeps every
+    `stride`-th pixel in y and x (each pixel depends on the whole network) plus per-view full-resolution moments."""
+    import time
+    enc, dec, head = vit_large_args()
+    torch.manual_seed(0)
+    model = Fast3R(dict(enc), dict(dec), dict(head)).eval()
+    shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    model.load_state_dict(synth_state_dict(shapes, seed=5))
+    N, B, H, W = 4, 1, 368, 512
+    imgs = synth_images(N, B, H, W)
+    views = [dict(img=imgs[i], true_shape=np.int32([[H, W]]), idx=i, instance=str(i), dataset="synthetic",
+                  label=f"v{i}") for i in range(N)]
+    torch.manual_seed(7)
+    t0 = time.time()
+    res = inference(views, model, torch.device("cpu"), dtype="32", verbose=False)
+    dt = time.time() - t0
+    preds = res["preds"]
+    sub = [{k: v[:, ::stride, ::stride].contiguous().clone() for k, v in p.items()} for p in preds]
+    mom = [{k: (float(v.double().mean()), float(v.double().std()), float(v.double().abs().max())) for k, v in p.items()}
+           for p in preds]
+    # calibration on this config: the reference's own bf16-autocast path vs its fp32 path
+    torch.manual_seed(7)
+    res16 = inference(views, model, torch.device("cpu"), dtype=torch.bfloat16, verbose=False)
+    gap = {}
+    for k in preds[0]:
+        a = torch.cat([p[k].float().flatten() for p in res16["preds"]])
+        b = torch.cat([p[k].float().flatten() for p in preds])
+        gap[k] = ((a - b).norm() / b.norm()).item()
+    out = dict(N=N, B=B, H=H, W=W, stride=stride, weight_seed=5, rng_seed=7, preds_sub=sub, moments=mom,
+               ref_bf16_vs_fp32_relL2=gap, ref_cpu_seconds=dt, ref_cpu_threads=torch.get_num_threads())
+    torch.save(out, os.path.join(HERE, f"{tag}.pt"))
+    print(tag, "saved", os.path.getsize(os.path.join(HERE, f"{tag}.pt")) / 1e6, "MB;", f"{dt:.1f} s on",
+          torch.get_num_threads(), "threads; ref bf16 vs fp32 gap", gap)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "vitl_n4":
+        run_vitl_n4()
+        sys.exit(0)
     run_tiny(1, 3, 64, 96, "tiny_b1_n3")
     run_tiny(2, 2, 48, 64, "tiny_b2_n2")
     # configuration quirks the replacement must honour (SURVEY.md Q3 / Q14 / Q16)
@@ -165,3 +205,4 @@ if __name__ == "__main__":
     run_tiny_mixed()
     run_tiny(1, 3, 32, 48, "tiny_trainmode", train_mode=True)
     run_blocks()
+    run_vitl_n4()

@@ -224,7 +224,100 @@ def check_cast(n=4096 * 3, seed=140):
     return float((out.float() - x.to(torch.bfloat16).float()).abs().max()), 1e-9, {}
 
 
+# ---------------------------------------------------------------- parity path (hi/lo-split bf16 products, fp32 storage)
+def _pack_x3(w):  # (N, taps, K) fp32 -> bf16 [Whi | Whi | Wlo]  (same packing as fast3r_b200.model._pk)
+    hi = w.to(torch.bfloat16)
+    lo = (w - hi.float()).to(torch.bfloat16)
+    return torch.cat([hi, hi, lo], dim=-1).contiguous()
+
+
+def check_split3(rows=300, k=200, seed=200):
+    x = _rand((rows, k), seed, 3.0, torch.float32)
+    out = torch.zeros(rows, 3 * k, dtype=torch.bfloat16, device="cuda")
+    ops.split3(x, out, relu=True)
+    v = F.relu(x)
+    hi = v.to(torch.bfloat16)
+    lo = (v - hi.float()).to(torch.bfloat16)
+    ref = torch.cat([hi, lo, hi], -1)
+    exact = float((out.float() - ref.float()).abs().max())
+    recon = rel(out[:, :k].float() + out[:, k:2 * k].float(), v)
+    return max(exact, recon / 1e-5 * 1e-9), 1e-9, dict(recon=recon)
+
+
+def check_linear_x3(M=1000, K=1024, N=512, seed=210, act=L.ACT_NONE):
+    a = _rand((M, K), seed, 1.0, torch.float32)
+    w = _rand((N, 1, K), seed + 1, K ** -0.5, torch.float32)
+    bias = _rand((N,), seed + 2, 1.0, torch.float32)
+    out = torch.zeros(M, N, dtype=torch.float32, device="cuda")
+    ops.gemm_x3(a, _pack_x3(w), w=M, bias=bias, out0=out, act=act)
+    ref = (a.double() @ w[:, 0].double().T + bias.double())
+    if act == L.ACT_GELU:
+        ref = F.gelu(ref)
+    return rel(out, ref), 3e-5, {}
+
+
+def check_conv3x3_x3(nb=2, H=9, W=24, C=96, N=256, seed=220):
+    x = _rand((nb, H, W, C), seed, 1.0, torch.float32)
+    w = _rand((N, C, 3, 3), seed + 1, (9 * C) ** -0.5, torch.float32)
+    bias = _rand((N,), seed + 2, 1.0, torch.float32)
+    r0 = _rand((nb, H, W, N), seed + 3, 1.0, torch.float32)
+    out = torch.zeros(nb, H, W, N, dtype=torch.float32, device="cuda")
+    ops.gemm_x3(x, _pack_x3(w.permute(0, 2, 3, 1).reshape(N, 9, C)), a_relu=True, w=W, h=H, nb=nb, taps=9, bias=bias,
+                out0=out, res0=r0)
+    ref = F.conv2d(F.relu(x).double().permute(0, 3, 1, 2), w.double(), bias.double(), padding=1).permute(0, 2, 3, 1) + r0
+    return rel(out, ref), 3e-5, {}
+
+
+def check_attention_x3(batch=2, heads=2, sq=300, skv=736, scale=0.16019, seed=230, qscale=1.0):
+    D = heads * 64
+    q = _rand((batch * sq, D), seed, qscale, torch.float32)
+    kv = _rand((batch * skv, 2 * D), seed + 1, 1.0, torch.float32)
+    out = torch.zeros(batch * sq, D, dtype=torch.float32, device="cuda")
+    lse = torch.zeros(batch, heads, sq, dtype=torch.float32, device="cuda")
+    ops.attention_x3(q, kv, out, batch=batch, heads=heads, sq=sq, skv=skv, scale=scale, lse=lse)
+    qh = q.reshape(batch, sq, heads, 64).transpose(1, 2).double()
+    kh = kv[:, :D].reshape(batch, skv, heads, 64).transpose(1, 2).double()
+    vh = kv[:, D:].reshape(batch, skv, heads, 64).transpose(1, 2).double()
+    sc = (qh @ kh.transpose(-2, -1)) * scale
+    ref = (sc.softmax(-1) @ vh).transpose(1, 2).reshape(batch * sq, D)
+    return rel(out, ref), 5e-5, dict(lse=rel(lse, torch.logsumexp(sc, -1)), nan=bool(torch.isnan(out).any()))
+
+
+def check_upsample_f32(n=2, H=12, W=16, C=256, crop=True, seed=240):
+    x = _rand((n, H, W, C), seed, 1.0, torch.float32)
+    Ho, Wo = (2 * H - 1, 2 * W) if crop else (2 * H, 2 * W)
+    out = torch.zeros(n, Ho, Wo, C, dtype=torch.float32, device="cuda")
+    ops.upsample2x(x, out, n, H, W, C, Ho, Wo)
+    ref = F.interpolate(x.permute(0, 3, 1, 2), scale_factor=2, mode="bilinear", align_corners=True)
+    return rel(out, ref[:, :, :Ho, :Wo].permute(0, 2, 3, 1)), 2e-6, {}
+
+
+def check_im2col_patch_f32(n=2, H=32, W=48, seed=250):
+    img = _rand((n, 3, H, W), seed, 1.0, torch.float32)
+    out = torch.zeros(n * (H // 16) * (W // 16), 768, dtype=torch.float32, device="cuda")
+    ops.im2col_patch(img, out)
+    ref = F.unfold(img, kernel_size=16, stride=16).transpose(1, 2).reshape(-1, 768)
+    return float((out - ref).abs().max()), 1e-9, {}
+
+
+def check_add_f32(n=4096 * 5, seed=260):
+    a, b = _rand((n,), seed, 1.0, torch.float32), _rand((n,), seed + 1, 1.0, torch.float32)
+    ref = a + b
+    ops.add_f32(a, b)
+    return float((a - ref).abs().max()), 1e-9, {}
+
+
 ALL = [
+    ("x3_split3", check_split3, {}),
+    ("x3_linear", check_linear_x3, {}),
+    ("x3_linear_gelu_tails", check_linear_x3, dict(M=333, K=256, N=96, act=L.ACT_GELU)),
+    ("x3_conv3x3_c96_relu_res", check_conv3x3_x3, {}),
+    ("x3_attn_tails", check_attention_x3, {}),
+    ("x3_attn_128", check_attention_x3, dict(batch=1, heads=1, sq=128, skv=128, scale=0.125)),
+    ("x3_attn_peaky_long", check_attention_x3, dict(batch=1, heads=2, sq=256, skv=4096, scale=0.5, qscale=3.0)),
+    ("x3_upsample_f32", check_upsample_f32, {}),
+    ("x3_im2col_patch_f32", check_im2col_patch_f32, {}),
+    ("x3_add_f32", check_add_f32, {}),
     ("cast", check_cast, {}),
     ("layernorm_1024", check_layernorm, {}),
     ("layernorm_128", check_layernorm, dict(rows=77, dim=128, eps=1e-6)),
@@ -254,4 +347,7 @@ ALL = [
     ("attn_24", check_attention, dict(batch=3, heads=2, sq=24, skv=24)),
     ("attn_long_3072", check_attention, dict(batch=1, heads=2, sq=512, skv=3072, scale=0.16019)),
     ("attn_peaky", check_attention, dict(batch=1, heads=2, sq=512, skv=2048, scale=0.5, qscale=3.0)),
+    # the bench regime: 23 552 keys (N=32 views) = 184 key blocks of lazy-rescale accumulation, flat and peaky scores
+    ("attn_skv23552", check_attention, dict(batch=1, heads=2, sq=512, skv=23552, scale=0.16019)),
+    ("attn_skv23552_peaky", check_attention, dict(batch=1, heads=1, sq=256, skv=23552, scale=0.5, qscale=3.0)),
 ]

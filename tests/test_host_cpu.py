@@ -63,7 +63,7 @@ def test_cabi_exports_every_declared_symbol():
     lib = ctypes.CDLL(L.LIB_PATH)
     for name in declared:
         assert hasattr(lib, name), name
-    assert L.load().f3r_abi_version() == 1
+    assert L.load().f3r_abi_version() == L.ABI_VERSION == 2
     assert L.load().f3r_gemm_desc_size() == ctypes.sizeof(L.GemmDesc) == 208
 
 

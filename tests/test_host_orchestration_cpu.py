@@ -84,8 +84,61 @@ def test_inference_api_structure(emulated, golden_dir):
             assert rel_l2(p[k], q[k]) < 2e-2
 
 
+# ------------------------------------------------------------------ parity path (precision="fp32") host wiring
+PARITY_TOL = 1e-3  # north star: pointmaps within 1e-3 rel-L2 of the reference's fp32 path
+
+
+@pytest.mark.parametrize("tag", ["tiny_b1_n3", "tiny_b2_n2", "tiny_nolocal_n2", "tiny_trainmode"])
+def test_parity_path_against_reference_fixture(emulated, golden_dir, tag):
+    """precision="fp32": fp32 activations, hi/lo-split bf16 products (emulated here with the same split arithmetic)."""
+    g = torch.load(os.path.join(golden_dir, f"{tag}.pt"))
+    model = _model(emulated, g).set_precision("fp32")
+    model.set_max_parallel_views_for_head(2)
+    imgs = synth_images(g["N"], g["B"], g["H"], g["W"])
+    torch.manual_seed(g["rng_seed"])
+    with torch.no_grad():
+        preds = model([dict(img=im) for im in imgs])
+    for k in g["preds"][0]:
+        a = torch.cat([p[k].flatten() for p in preds])
+        b = torch.cat([p[k].flatten() for p in g["preds"]])
+        assert preds[0][k].dtype == torch.float32
+        assert rel_l2(a, b) < PARITY_TOL, (tag, k, rel_l2(a, b))
+
+
+def test_parity_path_mixed_resolution(emulated, golden_dir):
+    g = torch.load(os.path.join(golden_dir, "tiny_mixed_res.pt"))
+    model = _model(emulated, g).set_precision("fp32")
+    imgs = [synth_images(1, g["B"], h, w, seed0=1234 + i)[0] for i, (h, w) in enumerate(g["sizes"])]
+    torch.manual_seed(g["rng_seed"])
+    preds = model([dict(img=im) for im in imgs])
+    for i, q in enumerate(g["preds"]):
+        for k in q:
+            assert rel_l2(preds[i][k], q[k]) < PARITY_TOL, (i, k, rel_l2(preds[i][k], q[k]))
+
+
+def test_inference_dtype_selects_precision(emulated, golden_dir):
+    """inference(dtype="32") and dtype=torch.float32 run the parity path, torch.bfloat16 the fast path
+    (reference: fast3r/dust3r/inference_multiview.py:41-49) and the model's own setting is restored afterwards."""
+    from fast3r_b200 import inference
+    from fast3r_b200.inference import precision_of
+    assert precision_of("32") == "fp32" and precision_of(torch.float32) == "fp32"
+    assert precision_of(torch.bfloat16) == "bf16" and precision_of("bf16") == "bf16" and precision_of(None) == "bf16"
+    g = torch.load(os.path.join(golden_dir, "tiny_nolocal_n2.pt"))
+    model = _model(emulated, g)
+    imgs = synth_images(g["N"], g["B"], g["H"], g["W"])
+    mk = lambda: [dict(img=im, true_shape=np.int32([[g["H"], g["W"]]]), idx=i, instance=str(i))  # noqa: E731
+                  for i, im in enumerate(imgs)]
+    err = {}
+    for dt in ("32", torch.bfloat16):
+        torch.manual_seed(g["rng_seed"])
+        res = inference(mk(), model, torch.device("cpu"), dtype=dt, verbose=False)
+        err[dt] = max(rel_l2(p[k], q[k]) for p, q in zip(res["preds"], g["preds"]) for k in q)
+        assert model.precision == "bf16"
+    assert err["32"] < PARITY_TOL < err[torch.bfloat16], err
+
+
 # ------------------------------------------------------------------ sequence parallel over gloo (2 ranks, CPU)
-def _sp_worker(rank, world, port, tag, golden_dir, ret):
+def _sp_worker(rank, world, port, tag, golden_dir, ret, seed_skew=0):
     import torch.distributed as dist
     import fast3r_b200.model as M
     from tests import abi_emulator
@@ -101,7 +154,8 @@ def _sp_worker(rank, world, port, tag, golden_dir, ret):
     torch.manual_seed(g["rng_seed"])
     ref = model(views)                                   # un-sharded forward in this process
     enable_sequence_parallel(model, gather_preds=True)
-    torch.manual_seed(g["rng_seed"])
+    # seed_skew != 0: ranks > 0 hold a DIFFERENT CPU RNG state; the ids of rank 0 must still be used everywhere
+    torch.manual_seed(g["rng_seed"] + seed_skew * rank)
     out = model(views)                                   # sharded over the 2 gloo ranks
     worst = max(rel_l2(torch.cat([p[k].flatten() for p in out]), torch.cat([p[k].flatten() for p in ref]))
                 for k in ref[0])
@@ -111,8 +165,8 @@ def _sp_worker(rank, world, port, tag, golden_dir, ret):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("tag", ["tiny_b1_n3", "tiny_b2_n2"])
-def test_sequence_parallel_forward_over_gloo(golden_dir, tag):
+@pytest.mark.parametrize("tag,seed_skew", [("tiny_b1_n3", 0), ("tiny_b2_n2", 0), ("tiny_b1_n3", 1000)])
+def test_sequence_parallel_forward_over_gloo(golden_dir, tag, seed_skew):
     """2-rank sharded forward vs the un-sharded forward of the same process and vs the reference fixture.  (On the
     GPU the two are bit-identical, tools/sp_check.py; the torch-CPU emulator's matmuls round differently for different
     shapes, so a small tolerance is used here.)"""
@@ -121,7 +175,7 @@ def test_sequence_parallel_forward_over_gloo(golden_dir, tag):
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     ctx = mp.get_context("spawn")
     ret = ctx.Manager().dict()
-    procs = [ctx.Process(target=_sp_worker, args=(r, 2, port, tag, golden_dir, ret)) for r in range(2)]
+    procs = [ctx.Process(target=_sp_worker, args=(r, 2, port, tag, golden_dir, ret, seed_skew)) for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:

@@ -74,3 +74,30 @@ def test_vitl_width_blocks(golden_dir):
     assert rel_l2(O.block(xd, sd, "", 16, 1e-5, 64 ** -0.5, None), g["dec_block_train"]) < TOL
     assert rel_l2(O.rope2d(g["rope_q"], pos), g["rope_out"]) < 1e-6
     assert abs(O.attn_bias_scale(64) - 0.16019) < 1e-5
+
+
+def vitl_n4_model_inputs(g):
+    """ViT-L state dict + views of the vitl_n4_368x512 fixture (BASELINE.json configs[0])."""
+    from fast3r_b200 import Fast3R, vit_large_args
+    enc, dec, head = vit_large_args()
+    with torch.device("meta"):
+        shapes = {k: tuple(v.shape) for k, v in Fast3R(enc, dec, head).state_dict().items()}
+    sd = synth_state_dict(shapes, seed=g["weight_seed"])
+    imgs = synth_images(g["N"], g["B"], g["H"], g["W"])
+    return (enc, dec, head), sd, imgs
+
+
+def test_vitl_n4_368x512_config0(golden_dir):
+    """Full ViT-L/512, N=4 views 512x368 (BASELINE configs[0]): oracle vs the reference's own inference(dtype="32")
+    output (every 4th pixel is stored; per-view full-resolution moments are checked too)."""
+    g = torch.load(os.path.join(golden_dir, "vitl_n4_368x512.pt"))
+    cfg, sd, imgs = vitl_n4_model_inputs(g)
+    torch.manual_seed(g["rng_seed"])
+    preds = O.forward(sd, *cfg, imgs)
+    st = g["stride"]
+    for i, (p, q) in enumerate(zip(preds, g["preds_sub"])):
+        for k in q:
+            assert rel_l2(p[k][:, ::st, ::st], q[k]) < TOL, (i, k, rel_l2(p[k][:, ::st, ::st], q[k]))
+            mean, std, amax = g["moments"][i][k]
+            assert abs(float(p[k].double().mean()) - mean) < 1e-4 * max(abs(mean), std)
+            assert abs(float(p[k].double().std()) - std) < 1e-4 * std
