@@ -1,9 +1,10 @@
 """Import harness for the UNMODIFIED reference (facebookresearch/fast3r @ /root/reference).
 
-TEST INFRASTRUCTURE ONLY. This file is used in the build container to (a) validate the
+TEST / BENCH INFRASTRUCTURE ONLY. This file is used in the build container to (a) validate the
 oracle restatement in ``oracle/fast3r_oracle.py`` and (b) generate the golden fixtures under
-``tests/golden/``.  ``/root/reference`` does not exist on the GPU box, so nothing that runs
-there (``-m gpu`` tests, ``smoke()``, ``bench.py``) may import this module.
+``tests/golden/``; and by ``bench.py --impl reference`` / the library-bar leg to run the reference itself.
+``/root/reference`` does not exist on the GPU box: there the harness falls back to ``oracle/_ref`` (a verbatim,
+git-ignored copy of the hot-path modules made by ``oracle/make_ref.py``).  The product never imports this module.
 
 Two in-memory stubs are needed because ``fast3r/models/fast3r.py:13`` imports omegaconf and
 ``fast3r/utils/__init__.py:7-11`` pulls hydra/lightning.
@@ -14,7 +15,13 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("FAST3R_REFERENCE_ROOT", "/root/reference")
+def _default_root() -> str:
+    if os.path.isdir("/root/reference/fast3r"):
+        return "/root/reference"
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+REFERENCE_ROOT = os.environ.get("FAST3R_REFERENCE_ROOT") or _default_root()
 
 
 def reference_available() -> bool:
