@@ -242,6 +242,8 @@ def library_bar(n_views, dev, steps=3, warmup=2):
             return {"unavailable": "no reference copy (oracle/_ref missing)"}
         model, ref_inference = ref
         views = make_views(n_views, device=dev)
+        for v in views:  # Fast3R.forward (unlike inference()) does not collate: it wants tensors
+            v["true_shape"] = torch.from_numpy(v["true_shape"]).to(dev)
 
         def step():
             torch.manual_seed(7)

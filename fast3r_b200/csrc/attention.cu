@@ -19,11 +19,10 @@
 
 namespace f3r {
 
-// kSplit = threads per query row in the softmax (1: 8 softmax warps, 2: 16 softmax warps, better latency hiding)
-template <int kSplit> constexpr int att_threads() { return 128 + 256 * kSplit; }  // warpgroup 0: TMA + MMA (+2 idle)
+constexpr int ATT_THREADS = 384;  // warpgroup 0: TMA + MMA (+2 idle warps); warpgroups 1, 2: softmax of tile 0 / 1
 constexpr int ATT_STAGES = 4;
 constexpr int ATT_TILE_BYTES = 128 * 64 * 2;  // 16 KB: 128 rows x 64 bf16
-constexpr int ATT_SMEM_BYTES = (2 + 2 * ATT_STAGES) * ATT_TILE_BYTES + 1024 + 256 + 4096 /*row-max exchange*/;
+constexpr int ATT_SMEM_BYTES = (2 + 2 * ATT_STAGES) * ATT_TILE_BYTES + 1024 + 256;
 
 constexpr uint32_t TM_S0 = 0, TM_S1 = 128, TM_P0 = 256, TM_P1 = 320, TM_O0 = 384, TM_O1 = 448;
 
@@ -50,49 +49,47 @@ F3R_DEVICE void fadd2(float& d0, float& d1, float a0, float a1) {
       : "+f"(d0), "+f"(d1) : "f"(a0), "f"(a1));
 }
 
-F3R_DEVICE void fsub2(float& d0, float& d1, float a0, float a1, float b0, float b1) {  // a - b
-  asm("{ .reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mov.b64 rc, {%6,%6};\n\t"
-      "fma.rn.f32x2 rd, rb, rc, ra; mov.b64 {%0,%1}, rd; }"
-      : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(-1.0f));
-}
-F3R_DEVICE void fma2v(float& d0, float& d1, float a0, float a1, float b0, float b1, float c) {  // a*b + c
-  asm("{ .reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mov.b64 rc, {%6,%6};\n\t"
-      "fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0,%1}, rd; }"
-      : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c));
-}
-// exp2 of a pair on the FMA / ALU pipes instead of the 16-per-clock-per-SM special-function unit: round-to-nearest
-// split x = n + f (magic-number add), degree-3 minimax polynomial of 2^f on [-0.5, 0.5] (max rel. error 7.6e-5, far
-// below the bf16 rounding of P), exponent patched in with an integer add.  x is clamped at -126 (2^-126 ~ 0).
+// exp2 of a PAIR on the FMA / ALU pipes instead of the special-function unit (MUFU.EX2 issues 16 / clk / SM, which at
+// head_dim 64 is the binding unit of this kernel: 2 x 128 x 128 exponentials per key block = 2048 clk vs 1024 clk of
+// MMA).  Cody-Waite split x = n + f with a magic-number add (round to nearest, f in [-0.5, 0.5]), degree-3 minimax
+// polynomial of 2^f (max rel. error 7.6e-5, well below the bf16 rounding of P: 2e-3), exponent patched in with an
+// integer shift-add.  6 packed FMA-pipe instructions + 4 ALU instructions per pair against 2 MUFU (16 clk of XU time).
+// x is clamped at -126 (2^-126 ~ 0); the lazy-rescale rule bounds x from above by 8.
 F3R_DEVICE void exp2_emu2(float& e0, float& e1, float x0, float x1) {
-  x0 = fmaxf(x0, -126.f); x1 = fmaxf(x1, -126.f);
-  float t0 = x0, t1 = x1;
-  fadd2(t0, t1, 12582912.f, 12582912.f);        // t = x + 1.5*2^23: low mantissa bits hold round(x)
-  float r0 = t0, r1 = t1;
-  fadd2(r0, r1, -12582912.f, -12582912.f);      // r = round(x)
-  float f0, f1;
-  fsub2(f0, f1, x0, x1, r0, r1);                // f = x - r in [-0.5, 0.5]
-  float p0, p1;
-  fma2v(p0, p1, f0, f1, 0.05520550534f, 0.05520550534f, 0.2426139712f);
-  fma2v(p0, p1, p0, p1, f0, f1, 0.6932547688f);
-  fma2v(p0, p1, p0, p1, f0, f1, 0.9999276996f);
-  e0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
-  e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+  uint32_t t0, t1, p0, p1;
+  asm("{ .reg .b64 x, t, r, f, p, k;\n\t"
+      ".reg .f32 xa, xb;\n\t"
+      "max.f32 xa, %4, 0fC2FC0000;\n\t"            // -126.0
+      "max.f32 xb, %5, 0fC2FC0000;\n\t"
+      "mov.b64 x, {xa, xb};\n\t"
+      "mov.b64 k, {%6, %6};\n\t"
+      "add.rn.f32x2 t, x, k;\n\t"                  // t = x + 1.5*2^23: low mantissa bits hold round(x)
+      "sub.rn.f32x2 r, t, k;\n\t"                  // r = round(x)
+      "sub.rn.f32x2 f, x, r;\n\t"                  // f = x - r in [-0.5, 0.5]
+      "mov.b64 k, {%7, %7};\n\t"
+      "mov.b64 p, {%8, %8};\n\t"
+      "fma.rn.f32x2 p, f, k, p;\n\t"               // c3 f + c2
+      "mov.b64 k, {%9, %9};\n\t"
+      "fma.rn.f32x2 p, p, f, k;\n\t"               // .. f + c1
+      "mov.b64 k, {%10, %10};\n\t"
+      "fma.rn.f32x2 p, p, f, k;\n\t"               // .. f + c0
+      "mov.b64 {%0, %1}, t;\n\t"
+      "mov.b64 {%2, %3}, p; }"
+      : "=r"(t0), "=r"(t1), "=r"(p0), "=r"(p1)
+      : "f"(x0), "f"(x1), "f"(12582912.f), "f"(0.05520550534f), "f"(0.2426139712f), "f"(0.6932547688f),
+        "f"(0.9999276996f));
+  e0 = __uint_as_float(p0 + (t0 << 23));
+  e1 = __uint_as_float(p1 + (t1 << 23));
 }
-// bit k set: pair k of every 8 score pairs takes the FMA-pipe exp2.  Measured (profiles/r01_notes.md): in the isolated
-// softmax stream 25 % emulation is 12 % faster (2386 -> 2110 clk / iteration), but in the full kernel the decoder layer
-// at N=32 went from 2.70 ms to 2.99 ms, so it is compiled out by default (build with -DF3R_ATT_EMU_MASK=0x11 to try).
-// 1: deferred row max (one-pass softmax, see the loop); 0: classic max pass before the exponentials.
-// Measured at N=32: 3.06 ms per decoder layer vs 2.70 ms for the classic order (the early pv_done wait and the chunked
-// P stores cost more than the max pre-pass saves), so the classic order stays the default.
-#ifndef F3R_ATT_DEFER_MAX
-#define F3R_ATT_DEFER_MAX 0
-#endif
-#ifndef F3R_ATT_EMU_MASK
-#define F3R_ATT_EMU_MASK 0x0
-#endif
 
-template <int kSplit>
-__global__ void __launch_bounds__(att_threads<kSplit>(), 1)
+// kEmu of every 8 score pairs take the FMA-pipe exp2 (0: all on MUFU).  Spread patterns keep each group of four
+// consecutive pairs mixed so that the scheduler can interleave the two instruction streams.
+template <int kEmu> __host__ __device__ constexpr uint32_t emu_mask() {
+  return kEmu == 0 ? 0x00u : kEmu == 1 ? 0x10u : kEmu == 2 ? 0x44u : kEmu == 3 ? 0x92u : kEmu == 4 ? 0xAAu : 0xDAu;
+}
+
+template <int kEmu>
+__global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
                  const __grid_constant__ AttnArgs p) {
   extern __shared__ uint8_t smem_raw[];
@@ -111,7 +108,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   uint64_t* p_full = s_free + 2;                 // 2
   uint64_t* pv_done = p_full + 2;                // 2
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(pv_done + 2);
-  float* xbuf = reinterpret_cast<float*>(smem_v + ATT_STAGES * ATT_TILE_BYTES + 256);  // [tile][parity][half][128]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -132,8 +128,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
     }
     for (int t = 0; t < 2; ++t) {
-      mbar_init(&s_full[t], 1); mbar_init(&s_free[t], 128 * kSplit);
-      mbar_init(&p_full[t], 128 * kSplit); mbar_init(&pv_done[t], 1);
+      mbar_init(&s_full[t], 1); mbar_init(&s_free[t], 128);
+      mbar_init(&p_full[t], 128); mbar_init(&pv_done[t], 1);
     }
     fence_barrier_init();
   }
@@ -144,10 +140,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp < 4) {
-    // register budget (must balance inside the CTA's launch allocation):
-    //   kSplit 1: 384 thr x 168 = 64512 = 128 x 72 + 256 x 216      kSplit 2: 640 thr x 96 = 61440 = 128 x 64 + 512 x 104
-    if constexpr (kSplit == 1) asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
-    else asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+    // register budget (must balance inside the CTA's launch allocation): 384 thr x 168 = 64512 = 128 x 72 + 256 x 216
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
   if (warp == 0) {
     if (lane == 0) {
       // ===================== TMA producer =====================
@@ -224,152 +218,35 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     }
   }
   } else {
-    // ===================== softmax warps =====================
-    if constexpr (kSplit == 1) asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
-    else asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
-    constexpr int COLS = 128 / kSplit;      // score columns per thread
-    constexpr int OCOLS = 64 / kSplit;      // output columns per thread
-    const int sw = warp - 4;
-    const int t = sw / (4 * kSplit);        // query tile 0 / 1
-    const int half = (sw >> 2) % kSplit;    // which column slice of the row this thread owns
+    // ===================== softmax warps: one thread per query row, the whole 128-wide score row in registers
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    const int t = (warp - 4) >> 2;          // query tile 0 / 1
     const int quarter = warp & 3;           // TMEM lane quarter accessible to this warp
     const int row = quarter * 32 + lane;    // row in the 128-row tile
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
-    const uint32_t tm_s = tmem_base + lane_base + (t ? TM_S1 : TM_S0) + half * COLS;
-    const uint32_t tm_p = tmem_base + lane_base + (t ? TM_P1 : TM_P0) + half * (COLS / 2);
-    const uint32_t tm_o = tmem_base + lane_base + (t ? TM_O1 : TM_O0) + half * OCOLS;
+    const uint32_t tm_s = tmem_base + lane_base + (t ? TM_S1 : TM_S0);
+    const uint32_t tm_p = tmem_base + lane_base + (t ? TM_P1 : TM_P0);
+    const uint32_t tm_o = tmem_base + lane_base + (t ? TM_O1 : TM_O0);
     const float sl2 = p.scale_log2;
     float m_used = -INFINITY;  // raw-score reference max the exponentials are taken against
-    float l = 0.f;             // this thread's partial row sum
+    float l = 0.f;             // row sum
+    constexpr uint32_t kMask = emu_mask<kEmu>();
 
-    float mx_prev = -INFINITY;  // (deferred-max variant) raw row max of the previous key block
     for (int j = 0; j < nkv; ++j) {
-      if constexpr (kSplit == 1 && F3R_ATT_DEFER_MAX) {
-        // ---- one-pass variant: the exponentials of block j are taken against the reference max known BEFORE the block
-        // (decided from block j-1's max), so the row-max reduction runs inside the exp loop on the ALU pipe instead of
-        // as a serial pre-pass.  Exact: P_j, l and O always share one reference; the reference moves one block late.
-        // If block j overshoots the reference by more than 2^64 the block is recomputed against its own max.
-        mbar_wait(&s_full[t], j & 1);
-        tc_fence_after();
-        uint32_t s[128];
-        tmem_ld32(tm_s + 0, s + 0);
-        tmem_ld32(tm_s + 32, s + 32);
-        tmem_ld32(tm_s + 64, s + 64);
-        tmem_ld32(tm_s + 96, s + 96);
-        tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive(&s_free[t]);
-        if (j == nkv - 1) {
-          const int valid = p.skv - j * 128;
-          if (valid < 128) {
-#pragma unroll
-            for (int i = 0; i < 128; ++i)
-              if (i >= valid) s[i] = 0xff800000u;
-          }
-        }
-        auto rowmax = [&]() {
-          float a0 = max3(__uint_as_float(s[0]), __uint_as_float(s[1]), __uint_as_float(s[2]));
-          float a1 = max3(__uint_as_float(s[3]), __uint_as_float(s[4]), __uint_as_float(s[5]));
-          float a2 = __uint_as_float(s[6]), a3 = __uint_as_float(s[7]);
-#pragma unroll
-          for (int i = 8; i < 128; i += 8) {
-            a0 = max3(a0, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
-            a1 = max3(a1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
-            a2 = max3(a2, __uint_as_float(s[i + 4]), __uint_as_float(s[i + 5]));
-            a3 = max3(a3, __uint_as_float(s[i + 6]), __uint_as_float(s[i + 7]));
-          }
-          return fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
-        };
-        auto rescale_o = [&](float alpha) {  // O_t *= alpha (PV_{j-1} must have completed)
-          uint32_t o[32];
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            tmem_ld32(tm_o + 32 * c, o);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st32(tm_o + 32 * c, o);
-          }
-          tmem_st_wait();
-        };
-        if (j == 0) {
-          m_used = rowmax();  // the first block has no earlier reference
-        } else {
-          float alpha = 1.f;
-          const bool need = (mx_prev - m_used) * sl2 > 8.f;
-          if (need) {
-            alpha = ex2_approx((m_used - mx_prev) * sl2);
-            m_used = mx_prev;
-            l *= alpha;
-          }
-          mbar_wait(&pv_done[t], (j - 1) & 1);  // O_t quiescent and P_t consumed (needed before the P stores anyway)
-          tc_fence_after();
-          if (__any_sync(0xffffffffu, need)) rescale_o(alpha);
-        }
-        const float l_before = l;
-        float mxc0, mxc1;
-        auto exp_pass = [&](bool track) {
-          const float nm = -m_used * sl2;
-          float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
-          mxc0 = -INFINITY; mxc1 = -INFINITY;
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            uint32_t pk[16];
-#pragma unroll
-            for (int i = 32 * c; i < 32 * c + 32; i += 4) {
-              float x0, x1, x2, x3;
-              ffma2(x0, x1, __uint_as_float(s[i]), __uint_as_float(s[i + 1]), sl2, nm);
-              ffma2(x2, x3, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]), sl2, nm);
-              if (track) {
-                mxc0 = max3(mxc0, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
-                mxc1 = max3(mxc1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
-              }
-              const float e0 = ex2_approx(x0), e1 = ex2_approx(x1), e2 = ex2_approx(x2), e3 = ex2_approx(x3);
-              fadd2(l0, l1, e0, e1);
-              fadd2(l2, l3, e2, e3);
-              pk[(i - 32 * c) / 2] = pack_bf16(e0, e1);
-              pk[(i - 32 * c) / 2 + 1] = pack_bf16(e2, e3);
-            }
-            tmem_st16(tm_p + 16 * c, pk);
-          }
-          return (l0 + l1) + (l2 + l3);
-        };
-        float lsum = exp_pass(j > 0);
-        if (j > 0) {
-          const float mx_cur = fmaxf(mxc0, mxc1);
-          mx_prev = mx_cur;
-          const bool over = (mx_cur - m_used) * sl2 > 64.f;  // reference too stale for this block: redo it exactly
-          if (__any_sync(0xffffffffu, over)) {
-            float alpha = 1.f;
-            if (over) { alpha = ex2_approx((m_used - mx_cur) * sl2); m_used = mx_cur; }
-            l = l_before * alpha;
-            tmem_st_wait();
-            rescale_o(alpha);
-            lsum = exp_pass(false);
-          }
-        } else {
-          mx_prev = m_used;
-        }
-        l += lsum;
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(&p_full[t]);
-        continue;
-      }
       mbar_wait(&s_full[t], j & 1);
       tc_fence_after();
-      uint32_t s[COLS];
+      uint32_t s[128];
 #pragma unroll
-      for (int c = 0; c < COLS / 32; ++c) tmem_ld32(tm_s + 32 * c, s + 32 * c);
+      for (int c = 0; c < 4; ++c) tmem_ld32(tm_s + 32 * c, s + 32 * c);
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&s_free[t]);  // S_t may be overwritten by the next QK^T
 
       if (j == nkv - 1) {
-        const int valid = p.skv - j * 128 - half * COLS;
-        if (valid < COLS) {
+        const int valid = p.skv - j * 128;
+        if (valid < 128) {
 #pragma unroll
-          for (int i = 0; i < COLS; ++i)
+          for (int i = 0; i < 128; ++i)
             if (i >= valid) s[i] = 0xff800000u;  // -inf
         }
       }
@@ -377,20 +254,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       float mx1 = max3(__uint_as_float(s[3]), __uint_as_float(s[4]), __uint_as_float(s[5]));
       float mx2 = __uint_as_float(s[6]), mx3 = __uint_as_float(s[7]);
 #pragma unroll
-      for (int i = 8; i < COLS; i += 8) {
+      for (int i = 8; i < 128; i += 8) {
         mx0 = max3(mx0, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
         mx1 = max3(mx1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
         mx2 = max3(mx2, __uint_as_float(s[i + 4]), __uint_as_float(s[i + 5]));
         mx3 = max3(mx3, __uint_as_float(s[i + 6]), __uint_as_float(s[i + 7]));
       }
-      float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-      if constexpr (kSplit == 2) {
-        // combine the two half-row maxima (both threads must take the same rescale decision)
-        float* xb = xbuf + ((t * 2 + (j & 1)) * 2) * 128;
-        xb[half * 128 + row] = mx;
-        asm volatile("bar.sync %0, 256;" ::"r"(1 + t) : "memory");
-        mx = fmaxf(mx, xb[(half ^ 1) * 128 + row]);
-      }
+      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
       // lazy rescale: move the reference only if the max grew by more than 8 (log2 domain)
       float alpha = 1.f;
       const bool need = (mx - m_used) * sl2 > 8.f;  // (-inf reference => true)
@@ -404,7 +274,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         tc_fence_after();
         uint32_t o[32];
 #pragma unroll
-        for (int c = 0; c < OCOLS / 32; ++c) {
+        for (int c = 0; c < 2; ++c) {
           tmem_ld32(tm_o + 32 * c, o);
           tmem_ld_wait();
 #pragma unroll
@@ -415,16 +285,16 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       }
       const float nm = -m_used * sl2;
       float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
-      uint32_t pk[COLS / 2];
+      uint32_t pk[64];
 #pragma unroll
-      for (int i = 0; i < COLS; i += 4) {
+      for (int i = 0; i < 128; i += 4) {
         float x0, x1, x2, x3;
         ffma2(x0, x1, __uint_as_float(s[i]), __uint_as_float(s[i + 1]), sl2, nm);
         ffma2(x2, x3, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]), sl2, nm);
         float e0, e1, e2, e3;
-        if ((F3R_ATT_EMU_MASK >> ((i / 2) & 7)) & 1) exp2_emu2(e0, e1, x0, x1);
+        if ((kMask >> ((i / 2) & 7)) & 1) exp2_emu2(e0, e1, x0, x1);
         else { e0 = ex2_approx(x0); e1 = ex2_approx(x1); }
-        if ((F3R_ATT_EMU_MASK >> ((i / 2 + 1) & 7)) & 1) exp2_emu2(e2, e3, x2, x3);
+        if ((kMask >> ((i / 2 + 1) & 7)) & 1) exp2_emu2(e2, e3, x2, x3);
         else { e2 = ex2_approx(x2); e3 = ex2_approx(x3); }
         fadd2(l0, l1, e0, e1);
         fadd2(l2, l3, e2, e3);
@@ -436,28 +306,21 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         mbar_wait(&pv_done[t], (j - 1) & 1);  // previous PV has consumed P_t
         tc_fence_after();
       }
-#pragma unroll
-      for (int c = 0; c < COLS / 64; ++c) tmem_st32(tm_p + 32 * c, pk + 32 * c);
+      tmem_st32(tm_p, pk);
+      tmem_st32(tm_p + 32, pk + 32);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&p_full[t]);
     }
 
     // ---- epilogue: O / l -> bf16 -> global
-    if constexpr (kSplit == 2) {
-      float* xb = xbuf + ((t * 2 + (nkv & 1)) * 2) * 128;  // slot not used by the last iteration's exchange
-      xb[half * 128 + row] = l;
-      asm volatile("bar.sync %0, 256;" ::"r"(1 + t) : "memory");
-      l += xb[(half ^ 1) * 128 + row];
-    }
     mbar_wait(&pv_done[t], (nkv - 1) & 1);
     tc_fence_after();
     const int q = qt * 256 + t * 128 + row;
     const float inv = 1.f / l;
-    __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.out) + (static_cast<size_t>(b) * p.sq + q) * p.ldo + h * 64 +
-                         half * OCOLS;
+    __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.out) + (static_cast<size_t>(b) * p.sq + q) * p.ldo + h * 64;
 #pragma unroll
-    for (int c = 0; c < OCOLS / 32; ++c) {
+    for (int c = 0; c < 2; ++c) {
       uint32_t o[32];
       tmem_ld32(tm_o + 32 * c, o);
       tmem_ld_wait();
@@ -474,7 +337,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         }
       }
     }
-    if (p.lse != nullptr && q < p.sq && half == 0)
+    if (p.lse != nullptr && q < p.sq)
       p.lse[(static_cast<size_t>(b) * p.heads + h) * p.sq + q] = m_used * sl2 * 0.69314718056f + logf(l);
   }
 
@@ -487,30 +350,39 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   }
 }
 
-template <int kSplit>
+template <int kEmu>
 static cudaError_t launch_attention_t(const CUtensorMap& tq, const CUtensorMap& tkv, const AttnArgs& a,
                                       cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attention_kernel<kSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         ATT_SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  // (set on every launch: the attribute is per device and one process may drive several GPUs)
+  cudaError_t e = cudaFuncSetAttribute(attention_kernel<kEmu>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       ATT_SMEM_BYTES);
+  if (e != cudaSuccess) return e;
   const int grid = a.batch * a.heads * a.q_tiles;
-  attention_kernel<kSplit><<<grid, att_threads<kSplit>(), ATT_SMEM_BYTES, stream>>>(tq, tkv, a);
+  attention_kernel<kEmu><<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tq, tkv, a);
   return cudaGetLastError();
 }
 
+#ifndef F3R_ATT_EMU_DEFAULT
+#define F3R_ATT_EMU_DEFAULT 0
+#endif
+
+int g_attn_emu = -1;  // f3r_set_option("attn_emu", v)
+
 cudaError_t launch_attention(const CUtensorMap& tq, const CUtensorMap& tkv, const AttnArgs& a, cudaStream_t stream) {
-  static int variant = -1;
-  if (variant < 0) {
-    // default: one thread per score row (measured 2.68 ms vs 3.11 ms per decoder layer at N=32 for the
-    // two-threads-per-row variant, profiles/r01_notes.md); F3R_ATTN_SPLIT=2 selects the latter for experiments
-    const char* e = getenv("F3R_ATTN_SPLIT");
-    variant = (e && e[0] == '2') ? 2 : 1;
+  // kEmu of every 8 exponential pairs on the FMA pipe; F3R_ATTN_EMU=0..5 (or f3r_set_option) overrides the default
+  // for A/B measurements
+  if (g_attn_emu < 0) {
+    const char* e = getenv("F3R_ATTN_EMU");
+    g_attn_emu = (e && e[0] >= '0' && e[0] <= '5') ? (e[0] - '0') : F3R_ATT_EMU_DEFAULT;
   }
-  return variant == 1 ? launch_attention_t<1>(tq, tkv, a, stream) : launch_attention_t<2>(tq, tkv, a, stream);
+  switch (g_attn_emu) {
+    case 1: return launch_attention_t<1>(tq, tkv, a, stream);
+    case 2: return launch_attention_t<2>(tq, tkv, a, stream);
+    case 3: return launch_attention_t<3>(tq, tkv, a, stream);
+    case 4: return launch_attention_t<4>(tq, tkv, a, stream);
+    case 5: return launch_attention_t<5>(tq, tkv, a, stream);
+    default: return launch_attention_t<0>(tq, tkv, a, stream);
+  }
 }
 
 }  // namespace f3r

@@ -82,6 +82,16 @@ int f3r_abi_version(void) { return F3R_ABI_VERSION; }
 size_t f3r_gemm_desc_size(void) { return sizeof(f3r_gemm_desc); }
 uint64_t f3r_launch_count(void) { return g_launches.load(); }
 
+int f3r_set_option(const char* name, int32_t value) {
+  if (!name) return fail("f3r_set_option: null name");
+  if (!strcmp(name, "attn_emu")) {
+    if (value < -1 || value > 5) return fail("f3r_set_option: attn_emu must be in [-1, 5]");
+    f3r::g_attn_emu = value;
+    return 0;
+  }
+  return fail("f3r_set_option: unknown option '%s'", name);
+}
+
 int f3r_gemm(const f3r_gemm_desc* d, void* stream) {
   if (!d || !d->a || !d->wt) return fail("f3r_gemm: null operand");
   if (d->n <= 0 || d->k <= 0 || d->w <= 0 || d->h <= 0 || d->nb <= 0) return fail("f3r_gemm: bad shape");

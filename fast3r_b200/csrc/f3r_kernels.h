@@ -50,6 +50,7 @@ struct AttnArgs {
   float* lse;                 // optional fp32 [batch, heads, sq] log-sum-exp (natural log)
 };
 cudaError_t launch_attention(const CUtensorMap& tq, const CUtensorMap& tkv, const AttnArgs& a, cudaStream_t stream);
+extern int g_attn_emu;  // exponential pairs (of every 8) evaluated on the FMA pipe, -1 = default
 
 // parity mode (attention_x3.cu): hi/lo-split bf16 operands, fp32 out (AttnArgs.out is float*, q_tiles = ceil(sq / 128))
 cudaError_t launch_attention_x3(const CUtensorMap& tq3, const CUtensorMap& tk3, const CUtensorMap& tv2,

@@ -76,6 +76,10 @@ size_t f3r_gemm_desc_size(void);
 /* Number of kernels launched through this library by the calling process so far. */
 uint64_t f3r_launch_count(void);
 
+/* Tuning knobs for A/B measurements (process-wide).  "attn_emu" = how many of every 8 exponential pairs of the
+ * attention softmax are evaluated on the FMA pipe instead of MUFU.EX2 (0..5, -1 = built-in default). */
+int f3r_set_option(const char* name, int32_t value);
+
 int f3r_gemm(const f3r_gemm_desc* d, void* stream);
 
 /* softmax(scale * Q K^T) V per (batch, head), head_dim 64, non-causal (blocks.py:135-194).

@@ -135,7 +135,7 @@ def test_vitl_n4_368x512_vs_reference_golden(golden_dir):
                 assert abs(float(p[k].double().std()) - std) < (1e-3 if dt == "32" else 5e-2) * std, (dt, i, k)
     print("vitl_n4_368x512", rep, "reference's own bf16-vs-fp32 gap:", g["ref_bf16_vs_fp32_relL2"])
     assert all(v <= PARITY_TOL for v in rep["32"].values()), rep
-    assert all(v <= 1e-2 for v in rep[str(torch.bfloat16)].values()), rep
+    assert all(v <= BF16_TOL for v in rep[str(torch.bfloat16)].values()), rep
 
 
 def test_vitl_n4_368x512_vs_oracle(golden_dir):
@@ -162,7 +162,7 @@ def test_vitl_n4_368x512_vs_oracle(golden_dir):
                      for k in ref[0]}
     print("vitl_n4 vs oracle", rep)
     assert all(v <= PARITY_TOL for v in rep["fp32"].values()), rep
-    assert all(v <= 1e-2 for v in rep["bf16"].values()), rep
+    assert all(v <= BF16_TOL for v in rep["bf16"].values()), rep
 
 
 def test_mixed_resolution_vs_reference_golden(golden_dir):
