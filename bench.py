@@ -162,6 +162,7 @@ def reference_model(device="cpu"):
     torch.manual_seed(0)
     with torch.device(device):
         model = RefFast3R(dict(enc), dict(dec), dict(head)).eval()
+    model = model.to(device)  # buffers built from numpy (image_idx_emb) ignore the device context
     return model, ref_inference
 
 

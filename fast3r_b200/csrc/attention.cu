@@ -9,7 +9,7 @@
 // Softmax is exact online softmax in fp32 (exp2 domain) with lazy O rescaling: the running reference max is
 // only moved when the row max grows by more than 2^8, which makes the TMEM read-modify-write of O rare.
 //
-// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread), warps 4-7 = softmax of tile 0,
+// Warp roles: warp 0 = TMA producer, warps 1 / 2 = MMA issuers of tile 0 / 1 (one elected thread each), warps 4-7 = softmax of tile 0,
 // warps 8-11 = softmax of tile 1 (one thread per query row).  setmaxnreg moves registers from warpgroup 0
 // to the softmax warpgroups, which keep a whole 128-wide score row in registers.
 #include <cstdlib>
@@ -124,8 +124,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     tma_prefetch_desc(&tmap_kv);
     mbar_init(q_full, 1);
     for (int s = 0; s < ATT_STAGES; ++s) {
-      mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1);
-      mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
+      mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 2);  // released by the MMA issuers of both tiles
+      mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 2);
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(&s_full[t], 1); mbar_init(&s_free[t], 128);
@@ -159,61 +159,52 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         if (++stage == ATT_STAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || warp == 2) {
     if (lane == 0) {
-      // ===================== MMA issuer =====================
+      // ===================== MMA issuers: warp 1 drives query tile 0, warp 2 query tile 1 =====================
+      // One issuing thread PER TILE: S_t(j+1) goes out as soon as the softmax warps of tile t hold S_t(j) in registers
+      // (s_free), independently of the other tile's P (with a single in-order issuer S_1(j+1) queued behind the wait for
+      // P_0(j) and the softmax warps spent 20 % of their time waiting for scores - ncu, profiles/r02_notes.md).
+      const int t = warp - 1;
       constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128, 0, 0);  // S[128x128] = Q[128x64] K^T, both K-major
       constexpr uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);   // O[128x64] += P[128x128] V, V MN-major
-      const uint64_t qdesc0 = make_smem_desc_sw128(smem_u32(smem_q), 1);
-      const uint64_t qdesc1 = make_smem_desc_sw128(smem_u32(smem_q + ATT_TILE_BYTES), 1);
-      auto issue_s = [&](int t, int stage) {
+      const uint64_t qd = make_smem_desc_sw128(smem_u32(smem_q + t * ATT_TILE_BYTES), 1);
+      const uint32_t tm_s = tmem_base + (t ? TM_S1 : TM_S0), tm_p = tmem_base + (t ? TM_P1 : TM_P0);
+      const uint32_t tm_o = tmem_base + (t ? TM_O1 : TM_O0);
+      auto issue_s = [&](int stage) {
         const uint64_t kdesc = make_smem_desc_sw128(smem_u32(smem_k + stage * ATT_TILE_BYTES), 1);
-        const uint64_t qd = t ? qdesc1 : qdesc0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_ss(tmem_base + (t ? TM_S1 : TM_S0), qd + 2 * k, kdesc + 2 * k, idesc_qk, k > 0 ? 1u : 0u);
+        for (int k = 0; k < 4; ++k) umma_ss(tm_s, qd + 2 * k, kdesc + 2 * k, idesc_qk, k > 0 ? 1u : 0u);
         umma_commit(&s_full[t]);
+        umma_commit(&k_empty[stage]);  // (count 2: both tiles have read this K block)
       };
-      auto issue_pv = [&](int t, int stage, int j) {
+      auto issue_pv = [&](int stage, int j) {
         const uint64_t vdesc = make_smem_desc_sw128(smem_u32(smem_v + stage * ATT_TILE_BYTES), 0);
 #pragma unroll
         for (int k = 0; k < 8; ++k)  // 16 keys per MMA: 8 packed-bf16 TMEM columns of P, 16 smem rows (2048 B) of V
-          umma_ts(tmem_base + (t ? TM_O1 : TM_O0), tmem_base + (t ? TM_P1 : TM_P0) + 8 * k, vdesc + 128 * k,
-                  idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+          umma_ts(tm_o, tm_p + 8 * k, vdesc + 128 * k, idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
         umma_commit(&pv_done[t]);
+        umma_commit(&v_empty[stage]);  // (count 2)
       };
       mbar_wait(q_full, 0);
       mbar_wait(&k_full[0], 0);
       tc_fence_after();
-      issue_s(0, 0);
-      issue_s(1, 0);
-      umma_commit(&k_empty[0]);
+      issue_s(0);
       for (int j = 0; j < nkv; ++j) {
         const int st = j % ATT_STAGES;
         const uint32_t ph = (j / ATT_STAGES) & 1;
-        const int st1 = (j + 1) % ATT_STAGES;
-        const uint32_t ph1 = ((j + 1) / ATT_STAGES) & 1;
-        const bool more = (j + 1) < nkv;
-        if (more) {
+        if (j + 1 < nkv) {
+          const int st1 = (j + 1) % ATT_STAGES;
+          const uint32_t ph1 = ((j + 1) / ATT_STAGES) & 1;
           mbar_wait(&k_full[st1], ph1);
-          mbar_wait(&s_free[0], j & 1);
+          mbar_wait(&s_free[t], j & 1);
           tc_fence_after();
-          issue_s(0, st1);
+          issue_s(st1);
         }
         mbar_wait(&v_full[st], ph);
-        mbar_wait(&p_full[0], j & 1);
+        mbar_wait(&p_full[t], j & 1);
         tc_fence_after();
-        issue_pv(0, st, j);
-        if (more) {
-          mbar_wait(&s_free[1], j & 1);
-          tc_fence_after();
-          issue_s(1, st1);
-          umma_commit(&k_empty[st1]);
-        }
-        mbar_wait(&p_full[1], j & 1);
-        tc_fence_after();
-        issue_pv(1, st, j);
-        umma_commit(&v_empty[st]);
+        issue_pv(st, j);
       }
     }
   }
