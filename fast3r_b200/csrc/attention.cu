@@ -19,10 +19,12 @@
 
 namespace f3r {
 
-constexpr int ATT_THREADS = 384;  // warpgroup 0: TMA + MMA (+2 idle warps); warpgroups 1, 2: softmax of tile 0 / 1
+// kSplit = softmax threads per query row: 1 (8 softmax warps, a whole 128-wide score row per thread) or 2 (16 softmax
+// warps = 4 per scheduler, 64 columns per thread: more warps to hide the fixed-latency stalls of the exp2 chains)
+template <int kSplit> constexpr int att_threads() { return 128 + 256 * kSplit; }  // warpgroup 0: TMA + 2 MMA issuers
 constexpr int ATT_STAGES = 4;
 constexpr int ATT_TILE_BYTES = 128 * 64 * 2;  // 16 KB: 128 rows x 64 bf16
-constexpr int ATT_SMEM_BYTES = (2 + 2 * ATT_STAGES) * ATT_TILE_BYTES + 1024 + 256;
+constexpr int ATT_SMEM_BYTES = (2 + 2 * ATT_STAGES) * ATT_TILE_BYTES + 1024 + 256 + 4096 /*half-row exchange*/;
 
 constexpr uint32_t TM_S0 = 0, TM_S1 = 128, TM_P0 = 256, TM_P1 = 320, TM_O0 = 384, TM_O1 = 448;
 
@@ -88,8 +90,8 @@ template <int kEmu> __host__ __device__ constexpr uint32_t emu_mask() {
   return kEmu == 0 ? 0x00u : kEmu == 1 ? 0x10u : kEmu == 2 ? 0x44u : kEmu == 3 ? 0x92u : kEmu == 4 ? 0xAAu : 0xDAu;
 }
 
-template <int kEmu>
-__global__ void __launch_bounds__(ATT_THREADS, 1)
+template <int kEmu, int kSplit>
+__global__ void __launch_bounds__(att_threads<kSplit>(), 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
                  const __grid_constant__ AttnArgs p) {
   extern __shared__ uint8_t smem_raw[];
@@ -108,15 +110,21 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   uint64_t* p_full = s_free + 2;                 // 2
   uint64_t* pv_done = p_full + 2;                // 2
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(pv_done + 2);
+  float* xbuf = reinterpret_cast<float*>(smem_v + ATT_STAGES * ATT_TILE_BYTES + 256);  // [tile][parity][half][128]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int qt = blockIdx.x % p.q_tiles;
-  const int bh = blockIdx.x / p.q_tiles;
+  // work item = (unit = (batch, head, 256-row query tile), split = slice of the key blocks of this launch's key range)
+  const int unit = blockIdx.x / p.n_split;
+  const int split = blockIdx.x % p.n_split;
+  const int qt = unit % p.q_tiles;
+  const int bh = unit / p.q_tiles;
   const int h = bh % p.heads;
   const int b = bh / p.heads;
-  const int nkv = (p.skv + 127) / 128;
+  const int nkv_all = (p.skv + 127) / 128;
+  const int j0 = static_cast<int>(static_cast<long long>(split) * nkv_all / p.n_split);  // first key block of this CTA
+  const int nkv = static_cast<int>(static_cast<long long>(split + 1) * nkv_all / p.n_split) - j0;  // (>= 1, host-checked)
   const int dmodel = p.heads * 64;
 
   if (threadIdx.x == 0) {
@@ -128,8 +136,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 2);
     }
     for (int t = 0; t < 2; ++t) {
-      mbar_init(&s_full[t], 1); mbar_init(&s_free[t], 128);
-      mbar_init(&p_full[t], 128); mbar_init(&pv_done[t], 1);
+      mbar_init(&s_full[t], 1); mbar_init(&s_free[t], 128 * kSplit);
+      mbar_init(&p_full[t], 128 * kSplit); mbar_init(&pv_done[t], 1);
     }
     fence_barrier_init();
   }
@@ -140,8 +148,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp < 4) {
-    // register budget (must balance inside the CTA's launch allocation): 384 thr x 168 = 64512 = 128 x 72 + 256 x 216
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+    // register budget (must balance inside the CTA's launch allocation):
+    //   kSplit 1: 384 thr x 168 = 64512 = 128 x 72 + 256 x 216      kSplit 2: 640 thr x 96 = 61440 = 128 x 64 + 512 x 104
+    if constexpr (kSplit == 1) asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+    else asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
   if (warp == 0) {
     if (lane == 0) {
       // ===================== TMA producer =====================
@@ -150,12 +160,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       tma_load_3d(smem_q + ATT_TILE_BYTES, &tmap_q, q_full, h * 64, qt * 256 + 128, b);
       int stage = 0; uint32_t phase = 0;
       for (int j = 0; j < nkv; ++j) {
-        mbar_wait(&k_empty[stage], phase ^ 1);
+        mbar_wait_relaxed(&k_empty[stage], phase ^ 1);
         mbar_arrive_expect_tx(&k_full[stage], ATT_TILE_BYTES);
-        tma_load_3d(smem_k + stage * ATT_TILE_BYTES, &tmap_kv, &k_full[stage], h * 64, j * 128, b);
-        mbar_wait(&v_empty[stage], phase ^ 1);
+        tma_load_3d(smem_k + stage * ATT_TILE_BYTES, &tmap_kv, &k_full[stage], h * 64, p.kv_row0 + (j0 + j) * 128, b);
+        mbar_wait_relaxed(&v_empty[stage], phase ^ 1);
         mbar_arrive_expect_tx(&v_full[stage], ATT_TILE_BYTES);
-        tma_load_3d(smem_v + stage * ATT_TILE_BYTES, &tmap_kv, &v_full[stage], dmodel + h * 64, j * 128, b);
+        tma_load_3d(smem_v + stage * ATT_TILE_BYTES, &tmap_kv, &v_full[stage], dmodel + h * 64,
+                    p.kv_row0 + (j0 + j) * 128, b);
         if (++stage == ATT_STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -209,35 +220,40 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     }
   }
   } else {
-    // ===================== softmax warps: one thread per query row, the whole 128-wide score row in registers
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
-    const int t = (warp - 4) >> 2;          // query tile 0 / 1
+    // ===================== softmax warps: kSplit threads per query row, 128 / kSplit score columns in registers
+    if constexpr (kSplit == 1) asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    constexpr int COLS = 128 / kSplit;      // score columns per thread
+    constexpr int OCOLS = 64 / kSplit;      // output columns per thread
+    const int sw = warp - 4;
+    const int t = sw / (4 * kSplit);        // query tile 0 / 1
+    const int half = (sw >> 2) % kSplit;    // which column slice of the row this thread owns
     const int quarter = warp & 3;           // TMEM lane quarter accessible to this warp
     const int row = quarter * 32 + lane;    // row in the 128-row tile
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
-    const uint32_t tm_s = tmem_base + lane_base + (t ? TM_S1 : TM_S0);
-    const uint32_t tm_p = tmem_base + lane_base + (t ? TM_P1 : TM_P0);
-    const uint32_t tm_o = tmem_base + lane_base + (t ? TM_O1 : TM_O0);
+    const uint32_t tm_s = tmem_base + lane_base + (t ? TM_S1 : TM_S0) + half * COLS;
+    const uint32_t tm_p = tmem_base + lane_base + (t ? TM_P1 : TM_P0) + half * (COLS / 2);
+    const uint32_t tm_o = tmem_base + lane_base + (t ? TM_O1 : TM_O0) + half * OCOLS;
     const float sl2 = p.scale_log2;
     float m_used = -INFINITY;  // raw-score reference max the exponentials are taken against
-    float l = 0.f;             // row sum
+    float l = 0.f;             // this thread's (partial) row sum
     constexpr uint32_t kMask = emu_mask<kEmu>();
 
     for (int j = 0; j < nkv; ++j) {
       mbar_wait(&s_full[t], j & 1);
       tc_fence_after();
-      uint32_t s[128];
+      uint32_t s[COLS];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld32(tm_s + 32 * c, s + 32 * c);
+      for (int c = 0; c < COLS / 32; ++c) tmem_ld32(tm_s + 32 * c, s + 32 * c);
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&s_free[t]);  // S_t may be overwritten by the next QK^T
 
-      if (j == nkv - 1) {
-        const int valid = p.skv - j * 128;
-        if (valid < 128) {
+      if (j0 + j == nkv_all - 1) {  // last key block of the launch's range: keys past its end are masked
+        const int valid = p.skv - (j0 + j) * 128 - half * COLS;
+        if (valid < COLS) {
 #pragma unroll
-          for (int i = 0; i < 128; ++i)
+          for (int i = 0; i < COLS; ++i)
             if (i >= valid) s[i] = 0xff800000u;  // -inf
         }
       }
@@ -245,13 +261,20 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       float mx1 = max3(__uint_as_float(s[3]), __uint_as_float(s[4]), __uint_as_float(s[5]));
       float mx2 = __uint_as_float(s[6]), mx3 = __uint_as_float(s[7]);
 #pragma unroll
-      for (int i = 8; i < 128; i += 8) {
+      for (int i = 8; i < COLS; i += 8) {
         mx0 = max3(mx0, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
         mx1 = max3(mx1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
         mx2 = max3(mx2, __uint_as_float(s[i + 4]), __uint_as_float(s[i + 5]));
         mx3 = max3(mx3, __uint_as_float(s[i + 6]), __uint_as_float(s[i + 7]));
       }
-      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      if constexpr (kSplit == 2) {
+        // combine the two half-row maxima (both threads must take the same rescale decision)
+        float* xb = xbuf + ((t * 2 + (j & 1)) * 2) * 128;
+        xb[half * 128 + row] = mx;
+        asm volatile("bar.sync %0, 256;" ::"r"(1 + t) : "memory");
+        mx = fmaxf(mx, xb[(half ^ 1) * 128 + row]);
+      }
       // lazy rescale: move the reference only if the max grew by more than 8 (log2 domain)
       float alpha = 1.f;
       const bool need = (mx - m_used) * sl2 > 8.f;  // (-inf reference => true)
@@ -265,7 +288,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         tc_fence_after();
         uint32_t o[32];
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
+        for (int c = 0; c < OCOLS / 32; ++c) {
           tmem_ld32(tm_o + 32 * c, o);
           tmem_ld_wait();
 #pragma unroll
@@ -276,9 +299,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       }
       const float nm = -m_used * sl2;
       float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
-      uint32_t pk[64];
+      uint32_t pk[COLS / 2];
 #pragma unroll
-      for (int i = 0; i < 128; i += 4) {
+      for (int i = 0; i < COLS; i += 4) {
         float x0, x1, x2, x3;
         ffma2(x0, x1, __uint_as_float(s[i]), __uint_as_float(s[i + 1]), sl2, nm);
         ffma2(x2, x3, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]), sl2, nm);
@@ -297,21 +320,49 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         mbar_wait(&pv_done[t], (j - 1) & 1);  // previous PV has consumed P_t
         tc_fence_after();
       }
-      tmem_st32(tm_p, pk);
-      tmem_st32(tm_p + 32, pk + 32);
+#pragma unroll
+      for (int c = 0; c < COLS / 64; ++c) tmem_st32(tm_p + 32 * c, pk + 32 * c);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&p_full[t]);
     }
 
     // ---- epilogue: O / l -> bf16 -> global
+    if constexpr (kSplit == 2) {
+      float* xb = xbuf + ((t * 2 + (nkv & 1)) * 2) * 128;  // slot not used by the last iteration's exchange
+      xb[half * 128 + row] = l;
+      asm volatile("bar.sync %0, 256;" ::"r"(1 + t) : "memory");
+      l += xb[(half ^ 1) * 128 + row];
+    }
     mbar_wait(&pv_done[t], (nkv - 1) & 1);
     tc_fence_after();
     const int q = qt * 256 + t * 128 + row;
     const float inv = 1.f / l;
-    __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.out) + (static_cast<size_t>(b) * p.sq + q) * p.ldo + h * 64;
+    if (p.part_o != nullptr) {
+      // partial result of this key slice: normalised fp32 O and its log-sum-exp; f3r_attention_merge combines slices
+      const size_t slot = static_cast<size_t>(p.part_base + split);
+      float* dstf = p.part_o + (slot * p.batch * p.sq + static_cast<size_t>(b) * p.sq + q) * dmodel + h * 64 + half * OCOLS;
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
+      for (int c = 0; c < OCOLS / 32; ++c) {
+        uint32_t o[32];
+        tmem_ld32(tm_o + 32 * c, o);
+        tmem_ld_wait();
+        if (q < p.sq) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            reinterpret_cast<float4*>(dstf + 32 * c)[i] =
+                make_float4(__uint_as_float(o[4 * i]) * inv, __uint_as_float(o[4 * i + 1]) * inv,
+                            __uint_as_float(o[4 * i + 2]) * inv, __uint_as_float(o[4 * i + 3]) * inv);
+        }
+      }
+      if (q < p.sq && half == 0)
+        p.part_lse[(slot * p.batch * p.heads + static_cast<size_t>(b) * p.heads + h) * p.sq + q] =
+            m_used * sl2 * 0.69314718056f + logf(l);
+    } else {
+    __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.out) + (static_cast<size_t>(b) * p.sq + q) * p.ldo + h * 64 +
+                         half * OCOLS;
+#pragma unroll
+    for (int c = 0; c < OCOLS / 32; ++c) {
       uint32_t o[32];
       tmem_ld32(tm_o + 32 * c, o);
       tmem_ld_wait();
@@ -328,8 +379,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         }
       }
     }
-    if (p.lse != nullptr && q < p.sq)
+    if (p.lse != nullptr && q < p.sq && half == 0)
       p.lse[(static_cast<size_t>(b) * p.heads + h) * p.sq + q] = m_used * sl2 * 0.69314718056f + logf(l);
+    }
   }
 
   tc_fence_before();
@@ -341,39 +393,90 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   }
 }
 
-template <int kEmu>
+template <int kEmu, int kSplit>
 static cudaError_t launch_attention_t(const CUtensorMap& tq, const CUtensorMap& tkv, const AttnArgs& a,
                                       cudaStream_t stream) {
   // (set on every launch: the attribute is per device and one process may drive several GPUs)
-  cudaError_t e = cudaFuncSetAttribute(attention_kernel<kEmu>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaError_t e = cudaFuncSetAttribute(attention_kernel<kEmu, kSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        ATT_SMEM_BYTES);
   if (e != cudaSuccess) return e;
-  const int grid = a.batch * a.heads * a.q_tiles;
-  attention_kernel<kEmu><<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tq, tkv, a);
+  const int grid = a.batch * a.heads * a.q_tiles * a.n_split;
+  attention_kernel<kEmu, kSplit><<<grid, att_threads<kSplit>(), ATT_SMEM_BYTES, stream>>>(tq, tkv, a);
   return cudaGetLastError();
 }
 
 #ifndef F3R_ATT_EMU_DEFAULT
-#define F3R_ATT_EMU_DEFAULT 0
+#define F3R_ATT_EMU_DEFAULT 1
+#endif
+#ifndef F3R_ATT_SPLIT_DEFAULT
+#define F3R_ATT_SPLIT_DEFAULT 2
 #endif
 
-int g_attn_emu = -1;  // f3r_set_option("attn_emu", v)
+int g_attn_emu = -1;    // f3r_set_option("attn_emu", v)
+int g_attn_split = -1;  // f3r_set_option("attn_split", v)
 
 cudaError_t launch_attention(const CUtensorMap& tq, const CUtensorMap& tkv, const AttnArgs& a, cudaStream_t stream) {
-  // kEmu of every 8 exponential pairs on the FMA pipe; F3R_ATTN_EMU=0..5 (or f3r_set_option) overrides the default
-  // for A/B measurements
+  // kEmu of every 8 exponential pairs on the FMA pipe, kSplit softmax threads per row; F3R_ATTN_EMU / F3R_ATTN_SPLIT
+  // (or f3r_set_option) override the defaults for A/B measurements
   if (g_attn_emu < 0) {
     const char* e = getenv("F3R_ATTN_EMU");
     g_attn_emu = (e && e[0] >= '0' && e[0] <= '5') ? (e[0] - '0') : F3R_ATT_EMU_DEFAULT;
   }
-  switch (g_attn_emu) {
-    case 1: return launch_attention_t<1>(tq, tkv, a, stream);
-    case 2: return launch_attention_t<2>(tq, tkv, a, stream);
-    case 3: return launch_attention_t<3>(tq, tkv, a, stream);
-    case 4: return launch_attention_t<4>(tq, tkv, a, stream);
-    case 5: return launch_attention_t<5>(tq, tkv, a, stream);
-    default: return launch_attention_t<0>(tq, tkv, a, stream);
+  if (g_attn_split < 0) {
+    const char* e = getenv("F3R_ATTN_SPLIT");
+    g_attn_split = (e && (e[0] == '1' || e[0] == '2')) ? (e[0] - '0') : F3R_ATT_SPLIT_DEFAULT;
   }
+#define F3R_ATT_CASE(E)                                                                       \
+  case E: return g_attn_split == 2 ? launch_attention_t<E, 2>(tq, tkv, a, stream)             \
+                                   : launch_attention_t<E, 1>(tq, tkv, a, stream);
+  switch (g_attn_emu) {
+    F3R_ATT_CASE(1) F3R_ATT_CASE(2) F3R_ATT_CASE(3) F3R_ATT_CASE(4) F3R_ATT_CASE(5)
+    default: return g_attn_split == 2 ? launch_attention_t<0, 2>(tq, tkv, a, stream)
+                                      : launch_attention_t<0, 1>(tq, tkv, a, stream);
+  }
+#undef F3R_ATT_CASE
+}
+
+// ---------------------------------------------------------------- merge of key-slice partials
+// out[row, h*64 + d] = sum_p w_p O_p[row, h, d] / sum_p w_p,  w_p = exp(lse_p - max_p lse_p): the exact softmax over the
+// union of the slices (each O_p is normalised over its own slice).  8 threads per (row, head), 8 columns each.
+__global__ void __launch_bounds__(256) attention_merge_kernel(const float* __restrict__ part_o,
+                                                              const float* __restrict__ part_lse, int n_parts, int batch,
+                                                              int heads, int sq, __nv_bfloat16* __restrict__ out, int ldo) {
+  const size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  const size_t rows = static_cast<size_t>(batch) * sq;
+  if (idx >= rows * heads * 8) return;
+  const int g = idx & 7;
+  const int h = (idx >> 3) % heads;
+  const size_t m = (idx >> 3) / heads;  // row = b * sq + q
+  const int b = static_cast<int>(m / sq), q = static_cast<int>(m % sq);
+  const int dm = heads * 64;
+  const size_t lse_i = (static_cast<size_t>(b) * heads + h) * sq + q, lse_stride = static_cast<size_t>(batch) * heads * sq;
+  float mx = -INFINITY;
+  for (int p = 0; p < n_parts; ++p) mx = fmaxf(mx, __ldg(part_lse + p * lse_stride + lse_i));
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float wsum = 0.f;
+  for (int p = 0; p < n_parts; ++p) {
+    const float w = __expf(__ldg(part_lse + p * lse_stride + lse_i) - mx);
+    wsum += w;
+    const float4* src = reinterpret_cast<const float4*>(part_o + (p * rows + m) * dm + h * 64 + g * 8);
+    const float4 a = __ldg(src), c = __ldg(src + 1);
+    acc[0] += w * a.x; acc[1] += w * a.y; acc[2] += w * a.z; acc[3] += w * a.w;
+    acc[4] += w * c.x; acc[5] += w * c.y; acc[6] += w * c.z; acc[7] += w * c.w;
+  }
+  const float inv = 1.f / wsum;
+  uint4 o;
+  o.x = pack_bf16(acc[0] * inv, acc[1] * inv); o.y = pack_bf16(acc[2] * inv, acc[3] * inv);
+  o.z = pack_bf16(acc[4] * inv, acc[5] * inv); o.w = pack_bf16(acc[6] * inv, acc[7] * inv);
+  *reinterpret_cast<uint4*>(out + m * ldo + h * 64 + g * 8) = o;
+}
+cudaError_t launch_attention_merge(const float* part_o, const float* part_lse, int n_parts, int batch, int heads, int sq,
+                                   void* out, int ldo, cudaStream_t stream) {
+  const size_t total = static_cast<size_t>(batch) * sq * heads * 8;
+  if (total == 0) return cudaSuccess;
+  attention_merge_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+      part_o, part_lse, n_parts, batch, heads, sq, static_cast<__nv_bfloat16*>(out), ldo);
+  return cudaGetLastError();
 }
 
 }  // namespace f3r

@@ -89,6 +89,11 @@ int f3r_set_option(const char* name, int32_t value) {
     f3r::g_attn_emu = value;
     return 0;
   }
+  if (!strcmp(name, "attn_split")) {
+    if (value != -1 && value != 1 && value != 2) return fail("f3r_set_option: attn_split must be -1, 1 or 2");
+    f3r::g_attn_split = value;
+    return 0;
+  }
   return fail("f3r_set_option: unknown option '%s'", name);
 }
 
@@ -203,12 +208,15 @@ int f3r_gemm(const f3r_gemm_desc* d, void* stream) {
                "f3r_gemm");
 }
 
-int f3r_attention(const void* q, int32_t ldq, const void* kv, int32_t ldkv, void* out, int32_t ldo, float* lse,
-                  int32_t batch, int32_t heads, int32_t sq, int32_t skv, float scale, void* stream) {
-  if (!q || !kv || !out) return fail("f3r_attention: null operand");
-  if (batch <= 0 || heads <= 0 || sq <= 0 || skv <= 0) return fail("f3r_attention: bad shape");
-  if (ldq % 8 || ldkv % 8 || ldo % 8 || ldq < heads * 64 || ldkv < 2 * heads * 64 || ldo < heads * 64)
-    return fail("f3r_attention: bad leading dimensions");
+static int attention_impl(const char* what, const void* q, int32_t ldq, const void* kv, int32_t ldkv,
+                          int32_t kv_rows_total, int32_t kv_row0, void* out, int32_t ldo, float* lse, float* part_o,
+                          float* part_lse, int32_t part_base, int32_t n_split, int32_t batch, int32_t heads, int32_t sq,
+                          int32_t skv, float scale, void* stream) {
+  if (!q || !kv) return fail("%s: null operand", what);
+  if (batch <= 0 || heads <= 0 || sq <= 0 || skv <= 0) return fail("%s: bad shape", what);
+  if (ldq % 8 || ldkv % 8 || ldq < heads * 64 || ldkv < 2 * heads * 64) return fail("%s: bad leading dimensions", what);
+  if (kv_row0 < 0 || kv_row0 + skv > kv_rows_total) return fail("%s: key range outside the kv buffer", what);
+  if (n_split < 1 || n_split > (skv + 127) / 128) return fail("%s: n_split=%d must be in [1, #key blocks]", what, n_split);
   CUtensorMap tq, tkv;
   {
     const uint64_t dims[3] = {static_cast<uint64_t>(heads) * 64, static_cast<uint64_t>(sq),
@@ -218,9 +226,9 @@ int f3r_attention(const void* q, int32_t ldq, const void* kv, int32_t ldkv, void
     if (make_tmap(&tq, q, 3, dims, str, box)) return 1;
   }
   {
-    const uint64_t dims[3] = {static_cast<uint64_t>(heads) * 128, static_cast<uint64_t>(skv),
+    const uint64_t dims[3] = {static_cast<uint64_t>(heads) * 128, static_cast<uint64_t>(kv_rows_total),
                               static_cast<uint64_t>(batch)};
-    const uint64_t str[2] = {static_cast<uint64_t>(ldkv) * 2, static_cast<uint64_t>(ldkv) * 2 * skv};
+    const uint64_t str[2] = {static_cast<uint64_t>(ldkv) * 2, static_cast<uint64_t>(ldkv) * 2 * kv_rows_total};
     const uint32_t box[3] = {64, 128, 1};
     if (make_tmap(&tkv, kv, 3, dims, str, box)) return 1;
   }
@@ -230,8 +238,34 @@ int f3r_attention(const void* q, int32_t ldq, const void* kv, int32_t ldkv, void
   a.q_tiles = (sq + 255) / 256;
   a.scale_log2 = scale * 1.4426950408889634f;
   a.ldo = ldo; a.out = out; a.lse = lse;
+  a.kv_row0 = kv_row0; a.n_split = n_split; a.part_base = part_base; a.part_o = part_o; a.part_lse = part_lse;
   g_launches++;
-  return check(f3r::launch_attention(tq, tkv, a, static_cast<cudaStream_t>(stream)), "f3r_attention");
+  return check(f3r::launch_attention(tq, tkv, a, static_cast<cudaStream_t>(stream)), what);
+}
+
+int f3r_attention(const void* q, int32_t ldq, const void* kv, int32_t ldkv, void* out, int32_t ldo, float* lse,
+                  int32_t batch, int32_t heads, int32_t sq, int32_t skv, float scale, void* stream) {
+  if (!out) return fail("f3r_attention: null operand");
+  if (ldo % 8 || ldo < heads * 64) return fail("f3r_attention: bad leading dimensions");
+  return attention_impl("f3r_attention", q, ldq, kv, ldkv, skv, 0, out, ldo, lse, nullptr, nullptr, 0, 1, batch, heads,
+                        sq, skv, scale, stream);
+}
+
+int f3r_attention_partial(const void* q, int32_t ldq, const void* kv, int32_t ldkv, int32_t kv_rows_total,
+                          int32_t kv_row0, int32_t skv, int32_t n_split, float* part_o, float* part_lse,
+                          int32_t part_base, int32_t batch, int32_t heads, int32_t sq, float scale, void* stream) {
+  if (!part_o || !part_lse || part_base < 0) return fail("f3r_attention_partial: bad partial buffers");
+  return attention_impl("f3r_attention_partial", q, ldq, kv, ldkv, kv_rows_total, kv_row0, nullptr, 0, nullptr, part_o,
+                        part_lse, part_base, n_split, batch, heads, sq, skv, scale, stream);
+}
+
+int f3r_attention_merge(const float* part_o, const float* part_lse, int32_t n_parts, void* out, int32_t ldo,
+                        int32_t batch, int32_t heads, int32_t sq, void* stream) {
+  if (!part_o || !part_lse || !out || n_parts < 1) return fail("f3r_attention_merge: bad arguments");
+  if (ldo % 8 || ldo < heads * 64) return fail("f3r_attention_merge: bad leading dimension");
+  g_launches++;
+  return check(f3r::launch_attention_merge(part_o, part_lse, n_parts, batch, heads, sq, out, ldo,
+                                           static_cast<cudaStream_t>(stream)), "f3r_attention_merge");
 }
 
 int f3r_layernorm(const float* x, const float* w, const float* b, void* out, int32_t out_f32, int32_t rows,

@@ -56,6 +56,12 @@ F3R_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Same, for waits that are not latency critical (TMA producers several stages ahead): sleeps between polls so that the
+// spinning warp does not take issue slots from the math warps that share its scheduler.
+F3R_DEVICE void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) asm volatile("nanosleep.u32 64;");
+}
+
 // ------------------------------------------------------------------ TMA loads (tile mode)
 F3R_DEVICE void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

@@ -48,9 +48,20 @@ struct AttnArgs {
   int ldo;                    // row stride of out (elements)
   void* out;                  // bf16 [batch*sq, ldo], head h at columns h*64
   float* lse;                 // optional fp32 [batch, heads, sq] log-sum-exp (natural log)
+  // key range of this launch inside the kv buffer: rows [kv_row0, kv_row0 + skv) of every batch
+  int kv_row0;
+  // key-slice partials: the key blocks are cut into n_split slices (one CTA each per query tile); with part_o != NULL
+  // slice s writes its normalised fp32 output / LSE into slot part_base + s (merged by launch_attention_merge)
+  int n_split;
+  int part_base;
+  float* part_o;              // fp32 [slots, batch*sq, heads*64]
+  float* part_lse;            // fp32 [slots, batch, heads, sq]
 };
+cudaError_t launch_attention_merge(const float* part_o, const float* part_lse, int n_parts, int batch, int heads, int sq,
+                                   void* out, int ldo, cudaStream_t stream);
 cudaError_t launch_attention(const CUtensorMap& tq, const CUtensorMap& tkv, const AttnArgs& a, cudaStream_t stream);
-extern int g_attn_emu;  // exponential pairs (of every 8) evaluated on the FMA pipe, -1 = default
+extern int g_attn_emu;    // exponential pairs (of every 8) evaluated on the FMA pipe, -1 = default
+extern int g_attn_split;  // softmax threads per query row (1 or 2), -1 = default
 
 // parity mode (attention_x3.cu): hi/lo-split bf16 operands, fp32 out (AttnArgs.out is float*, q_tiles = ceil(sq / 128))
 cudaError_t launch_attention_x3(const CUtensorMap& tq3, const CUtensorMap& tk3, const CUtensorMap& tv2,

@@ -413,12 +413,10 @@ class Fast3R(nn.Module):
                         rope_sin=rope["sin"])
         else:
             cls._linear(x3, h, w.qkv_w, w.qkv_b, out0=q, ldo=D, split_col=D, out0b=kv, ldo_b=2 * D)
-        attn = ops.attention_x3 if x3 else ops.attention
         if kv_exchange is None:
-            attn(q, kv, att, batch=batch, heads=heads, sq=seq, skv=seq, scale=scale)
-        else:
-            kv_all, skv = kv_exchange(kv)
-            attn(q, kv_all, att, batch=batch, heads=heads, sq=seq, skv=skv, scale=scale)
+            (ops.attention_x3 if x3 else ops.attention)(q, kv, att, batch=batch, heads=heads, sq=seq, skv=seq, scale=scale)
+        else:  # sequence parallel: exchange K|V with the other ranks and attend to all keys (parallel.KVExchange)
+            kv_exchange.attend(ops, q, kv, att, heads=heads, scale=scale, x3=x3)
         cls._linear(x3, att, w.proj_w, w.proj_b, out0=x, res0=x)
         ops.layernorm(x, w.n2w, w.n2b, eps, h)
         cls._linear(x3, h, w.fc1_w, w.fc1_b, out0=hid, act=L.ACT_GELU)
@@ -478,6 +476,10 @@ class Fast3R(nn.Module):
             scale = hd ** -0.5
         hidden = dec.dec_blocks[0].mlp.fc1.weight.shape[0]
         ws = self._workspace(M, D, hidden, dev, x3)
+        if kv_exchange is not None:
+            slot = kv_exchange.kv_workspace(ws["kv"].dtype, dev)
+            if slot is not None:
+                ws["kv"] = slot  # the QKV GEMM writes K|V straight into this rank's slot of the gather buffer
         depth = dec.depth
         hooks = {depth * 2 // 4: None, depth * 3 // 4: None}
         self._tap("dec_embed", x)

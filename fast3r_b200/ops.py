@@ -136,9 +136,54 @@ def linear(a: torch.Tensor, wt: torch.Tensor, bias=None, **kw):
     return gemm(a, wt, w=a.numel() // a.shape[-1], bias=bias, **kw)
 
 
+NUM_SMS = 148
+
+
+def pick_kv_split(units: int, key_blocks: int, max_split: int = 8) -> int:
+    """Key slices per (batch, head, 256-row query tile) unit so that units * slices CTAs fill whole waves of the 148
+    SMs (one CTA per SM): minimises ceil(units*s / 148) / s; every slice keeps >= 4 key blocks; 1 = no slicing."""
+    if units >= 3 * NUM_SMS:
+        return 1
+    best, best_cost = 1, None
+    for s_ in range(1, max_split + 1):
+        if s_ > 1 and key_blocks // s_ < 4:
+            break
+        cost = -(-units * s_ // NUM_SMS) / s_ * (1.0 + 0.01 * (s_ - 1))  # (+1 % per extra slice: merge + prologues)
+        if best_cost is None or cost < best_cost - 1e-9:
+            best, best_cost = s_, cost
+    return best
+
+
+def attention_partial(q: torch.Tensor, kv: torch.Tensor, part_o: torch.Tensor, part_lse: torch.Tensor, *, part_base: int,
+                      n_split: int, batch: int, heads: int, sq: int, kv_rows_total: int, kv_row0: int, skv: int,
+                      scale: float):
+    """Attends q to the keys [kv_row0, kv_row0 + skv) of kv (batch*kv_rows_total, ldkv), cut into n_split slices; slice s
+    fills slot part_base + s of part_o (slots, batch*sq, heads*64) fp32 / part_lse (slots, batch, heads, sq) fp32."""
+    _chk(q, BF16, "q"); _chk(kv, BF16, "kv"); _chk(part_o, F32, "part_o"); _chk(part_lse, F32, "part_lse")
+    ldq, ldkv = q.shape[-1], kv.shape[-1]
+    assert q.numel() == batch * sq * ldq and kv.numel() == batch * kv_rows_total * ldkv
+    slots = part_o.shape[0]
+    assert part_base + n_split <= slots and part_o.numel() == slots * batch * sq * heads * 64
+    assert part_lse.numel() == slots * batch * heads * sq
+    with _on_device(q):
+        L.check(L.load().f3r_attention_partial(_ptr(q), ldq, _ptr(kv), ldkv, kv_rows_total, kv_row0, skv, n_split,
+                                               _ptr(part_o), _ptr(part_lse), part_base, batch, heads, sq, float(scale),
+                                               _stream(q)), "f3r_attention_partial")
+
+
+def attention_merge(part_o: torch.Tensor, part_lse: torch.Tensor, n_parts: int, out: torch.Tensor, *, batch: int,
+                    heads: int, sq: int):
+    _chk(part_o, F32, "part_o"); _chk(part_lse, F32, "part_lse"); _chk(out, BF16, "out")
+    assert out.numel() == batch * sq * out.shape[-1] and n_parts <= part_o.shape[0]
+    with _on_device(out):
+        L.check(L.load().f3r_attention_merge(_ptr(part_o), _ptr(part_lse), n_parts, _ptr(out), out.shape[-1], batch,
+                                             heads, sq, _stream(out)), "f3r_attention_merge")
+
+
 def attention(q: torch.Tensor, kv: torch.Tensor, out: torch.Tensor, *, batch: int, heads: int, sq: int, skv: int,
-              scale: float, lse: Optional[torch.Tensor] = None):
-    """q (batch*sq, ldq) bf16, kv (batch*skv, ldkv) bf16 [K | V], out (batch*sq, ldo) bf16."""
+              scale: float, lse: Optional[torch.Tensor] = None, kv_split: Optional[int] = None):
+    """q (batch*sq, ldq) bf16, kv (batch*skv, ldkv) bf16 [K | V], out (batch*sq, ldo) bf16.  When the launch would
+    leave SMs idle (few query tiles), the keys are cut into slices (more CTAs) and merged (pick_kv_split)."""
     _chk(q, BF16, "q"); _chk(kv, BF16, "kv"); _chk(out, BF16, "out")
     ldq, ldkv, ldo = q.shape[-1], kv.shape[-1], out.shape[-1]
     assert q.numel() == batch * sq * ldq and kv.numel() == batch * skv * ldkv and out.numel() == batch * sq * ldo
@@ -147,9 +192,18 @@ def attention(q: torch.Tensor, kv: torch.Tensor, out: torch.Tensor, *, batch: in
     if timer is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(st)
-    with _on_device(q):
-        L.check(L.load().f3r_attention(_ptr(q), ldq, _ptr(kv), ldkv, _ptr(out), ldo, _ptr(lse), batch, heads, sq, skv,
-                                       float(scale), st.cuda_stream), "f3r_attention")
+    ns = kv_split if kv_split is not None else (
+        1 if lse is not None else pick_kv_split(batch * heads * ((sq + 255) // 256), (skv + 127) // 128))
+    if ns > 1:
+        part_o = torch.empty(ns, batch * sq, heads * 64, dtype=F32, device=q.device)
+        part_lse = torch.empty(ns, batch, heads, sq, dtype=F32, device=q.device)
+        attention_partial(q, kv, part_o, part_lse, part_base=0, n_split=ns, batch=batch, heads=heads, sq=sq,
+                          kv_rows_total=skv, kv_row0=0, skv=skv, scale=scale)
+        attention_merge(part_o, part_lse, ns, out, batch=batch, heads=heads, sq=sq)
+    else:
+        with _on_device(q):
+            L.check(L.load().f3r_attention(_ptr(q), ldq, _ptr(kv), ldkv, _ptr(out), ldo, _ptr(lse), batch, heads, sq, skv,
+                                           float(scale), st.cuda_stream), "f3r_attention")
     if timer is not None:
         e1.record(st)
         timer.append((batch, heads, sq, skv, e0, e1))

@@ -38,6 +38,89 @@ def assemble_kv(gathered: torch.Tensor, batch: int, rows: List[int]) -> torch.Te
     return torch.cat(parts, dim=1).reshape(-1, C)
 
 
+class KVExchange:
+    """K|V exchange + global attention of one sequence-parallel decoder forward.
+
+    Fast path (bf16 path, batch 1, equal shards): the QKV GEMM writes this rank's K|V straight into its slot of the
+    gather buffer (`kv_workspace()`); `attend()` starts the NCCL all-gather on a side stream and meanwhile attends the
+    local queries to the LOCAL keys; when the gather has landed it attends to the key ranges of the other ranks and merges
+    the partial results by their log-sum-exp (exact softmax over the union, f3r_attention_merge).  The exchange is hidden
+    behind the local-chunk attention and every launch is key-sliced to fill the 148 SMs (ops.pick_kv_split).
+    General path (batch > 1, uneven shards, parity precision, CPU emulator): all-gather, then one attention call."""
+
+    def __init__(self, sp, batch: int, s_local: int, dim: int, rows: List[int]):
+        self.sp, self.batch, self.s_local, self.dim, self.rows = sp, batch, s_local, dim, rows
+        self.mx, self.s_total = max(rows), sum(rows)
+        self.even = all(r == self.mx for r in rows)
+        self.buf = None
+        self.pad = None
+        self.comm_stream = None
+        self.parts = None
+
+    def _ensure(self, like: torch.Tensor):
+        if self.buf is None or self.buf.dtype != like.dtype or self.buf.device != like.device:
+            C = 2 * self.dim
+            self.buf = torch.empty(self.sp.world, self.batch * self.mx, C, dtype=like.dtype, device=like.device)
+            self.pad = None if self.even else torch.zeros(self.batch * self.mx, C, dtype=like.dtype, device=like.device)
+            if like.is_cuda:
+                self.comm_stream = torch.cuda.Stream(device=like.device)
+
+    def fast(self, dtype, device) -> bool:
+        return self.even and self.batch == 1 and dtype == torch.bfloat16 and device.type == "cuda" and self.sp.overlap
+
+    def kv_workspace(self, dtype, device):
+        """Where the QKV GEMM should write this rank's K|V (None: any buffer; attend() copies)."""
+        if not self.fast(dtype, device):
+            return None
+        self._ensure(torch.empty(0, dtype=dtype, device=device))
+        return self.buf[self.sp.rank]
+
+    def attend(self, ops, q, kv, att, *, heads: int, scale: float, x3: bool):
+        sp, C = self.sp, kv.shape[-1]
+        self._ensure(kv)
+        if not self.fast(kv.dtype, kv.device) or x3:
+            src = kv
+            if not self.even:
+                self.pad.view(self.batch, self.mx, C)[:, :self.s_local] = kv.view(self.batch, self.s_local, C)
+                src = self.pad
+            dist.all_gather_into_tensor(self.buf.view(-1, C), src.contiguous(), group=sp.group)
+            sp.bytes_exchanged += self.buf.numel() * self.buf.element_size()
+            kv_all = assemble_kv(self.buf, self.batch, self.rows)
+            (ops.attention_x3 if x3 else ops.attention)(q, kv_all, att, batch=self.batch, heads=heads, sq=self.s_local,
+                                                        skv=self.s_total, scale=scale)
+            return
+        # ---- overlapped path
+        slot = self.buf[sp.rank]
+        if kv.data_ptr() != slot.data_ptr():
+            slot.copy_(kv)
+        compute = torch.cuda.current_stream(kv.device)
+        self.comm_stream.wait_stream(compute)  # K|V of this layer is complete; previous layer's readers are done
+        with torch.cuda.stream(self.comm_stream):
+            dist.all_gather_into_tensor(self.buf.view(-1, C), slot, group=sp.group)
+        sp.bytes_exchanged += self.buf.numel() * self.buf.element_size()
+        S, sl = self.s_total, self.s_local
+        lo, hi = sp.rank * sl, (sp.rank + 1) * sl
+        units = heads * ((sl + 255) // 256)
+        ranges = [(lo, sl)] + [r for r in ((0, lo), (hi, S - hi)) if r[1] > 0]   # local keys first, then the others
+        splits = [ops.pick_kv_split(units, (n + 127) // 128) for _, n in ranges]
+        slots = sum(splits)
+        if self.parts is None or self.parts[0].shape[0] < slots:
+            self.parts = (torch.empty(slots, sl, heads * 64, dtype=torch.float32, device=kv.device),
+                          torch.empty(slots, 1, heads, sl, dtype=torch.float32, device=kv.device))
+        part_o, part_lse = self.parts
+        kv_all = self.buf.view(-1, C)
+        base = 0
+        for i, ((row0, n), ns) in enumerate(zip(ranges, splits)):
+            if i == 1:
+                compute.wait_stream(self.comm_stream)  # the other ranks' keys have landed
+            ops.attention_partial(q, kv_all, part_o, part_lse, part_base=base, n_split=ns, batch=1, heads=heads, sq=sl,
+                                  kv_rows_total=S, kv_row0=row0, skv=n, scale=scale)
+            base += ns
+        if len(ranges) == 1:
+            compute.wait_stream(self.comm_stream)
+        ops.attention_merge(part_o, part_lse, slots, att, batch=1, heads=heads, sq=sl)
+
+
 class SequenceParallel:
     def __init__(self, group=None, gather_preds: bool = True):
         if not dist.is_initialized():
@@ -46,6 +129,7 @@ class SequenceParallel:
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         self.gather_preds = gather_preds
+        self.overlap = True   # False: always all-gather first, then one attention call (A/B measurements)
         self._ranges = None
         self.bytes_exchanged = 0
 
@@ -67,29 +151,10 @@ class SequenceParallel:
         return t.cpu()
 
     def make_kv_exchange(self, batch: int, s_local: int, dim: int):
-        """Returns kv_exchange(kv_local (batch*s_local, 2*dim) bf16) -> (kv_all (batch*s_total, 2*dim), s_total)."""
+        """Per-forward exchange object for the fusion decoder (one per `_decode` call)."""
         tok_per_view = s_local // (self._ranges[self.rank][1] - self._ranges[self.rank][0])
         rows = [(hi - lo) * tok_per_view for lo, hi in self._ranges]
-        mx, s_total = max(rows), sum(rows)
-        even = all(r == mx for r in rows)
-        state = {}
-
-        def kv_exchange(kv_local: torch.Tensor):
-            C = kv_local.shape[-1]
-            if "buf" not in state:
-                state["buf"] = torch.empty(self.world, batch * mx, C, dtype=kv_local.dtype, device=kv_local.device)
-                state["pad"] = None if even else torch.zeros(batch * mx, C, dtype=kv_local.dtype,
-                                                             device=kv_local.device)
-            src = kv_local
-            if not even:
-                pad = state["pad"]
-                pad.view(batch, mx, C)[:, :s_local] = kv_local.view(batch, s_local, C)
-                src = pad
-            dist.all_gather_into_tensor(state["buf"].view(-1, C), src.contiguous(), group=self.group)
-            self.bytes_exchanged += state["buf"].numel() * state["buf"].element_size()
-            return assemble_kv(state["buf"], batch, rows), s_total
-
-        return kv_exchange
+        return KVExchange(self, batch, s_local, dim, rows)
 
     def gather_results(self, final_results, num_views, batch, H, W, device):
         """All ranks end up with the preds of every view (API parity with the single-device forward)."""

@@ -77,7 +77,8 @@ size_t f3r_gemm_desc_size(void);
 uint64_t f3r_launch_count(void);
 
 /* Tuning knobs for A/B measurements (process-wide).  "attn_emu" = how many of every 8 exponential pairs of the
- * attention softmax are evaluated on the FMA pipe instead of MUFU.EX2 (0..5, -1 = built-in default). */
+ * attention softmax are evaluated on the FMA pipe instead of MUFU.EX2 (0..5, -1 = built-in default); "attn_split" =
+ * softmax threads per query row (1 or 2, -1 = default). */
 int f3r_set_option(const char* name, int32_t value);
 
 int f3r_gemm(const f3r_gemm_desc* d, void* stream);
@@ -87,6 +88,18 @@ int f3r_gemm(const f3r_gemm_desc* d, void* stream);
  * h*64 and V at columns heads*64 + h*64; out: bf16 [batch, sq, ldo].  lse (optional): fp32 [batch, heads, sq]. */
 int f3r_attention(const void* q, int32_t ldq, const void* kv, int32_t ldkv, void* out, int32_t ldo, float* lse,
                   int32_t batch, int32_t heads, int32_t sq, int32_t skv, float scale, void* stream);
+
+/* Key-slice form of f3r_attention, for (a) filling the 148 SMs when batch*heads*ceil(sq/256) is small and (b) attending
+ * to key ranges as they arrive over NVLink (sequence-parallel decoder, fast3r_b200/parallel.py): attends the queries to
+ * the keys [kv_row0, kv_row0 + skv) of a kv buffer of kv_rows_total rows per batch, cut into n_split slices (one CTA each
+ * per 256-row query tile); slice s writes its softmax-normalised fp32 output into part_o[part_base + s] (layout
+ * [slot, batch*sq, heads*64]) and its log-sum-exp into part_lse[part_base + s] ([slot, batch, heads, sq]).
+ * f3r_attention_merge combines n_parts slots into the exact softmax over the union of their keys (bf16 out). */
+int f3r_attention_partial(const void* q, int32_t ldq, const void* kv, int32_t ldkv, int32_t kv_rows_total,
+                          int32_t kv_row0, int32_t skv, int32_t n_split, float* part_o, float* part_lse,
+                          int32_t part_base, int32_t batch, int32_t heads, int32_t sq, float scale, void* stream);
+int f3r_attention_merge(const float* part_o, const float* part_lse, int32_t n_parts, void* out, int32_t ldo,
+                        int32_t batch, int32_t heads, int32_t sq, void* stream);
 
 /* nn.LayerNorm over the last dim of fp32 x [rows, dim] -> bf16 (or fp32) out  (blocks.py:219,228; fast3r.py:558,805) */
 int f3r_layernorm(const float* x, const float* w, const float* b, void* out, int32_t out_f32, int32_t rows,

@@ -123,7 +123,7 @@ def attention_x3(q, kv, out, *, batch, heads, sq, skv, scale, lse=None):
         _store(lse, torch.logsumexp(s, -1))
 
 
-def attention(q, kv, out, *, batch, heads, sq, skv, scale, lse=None):
+def attention(q, kv, out, *, batch, heads, sq, skv, scale, lse=None, kv_split=None):
     D = heads * 64
     qh = q.reshape(batch, sq, heads, 64).transpose(1, 2).float()
     kh = kv[:, :D].reshape(batch, skv, heads, 64).transpose(1, 2).float()
@@ -133,6 +133,35 @@ def attention(q, kv, out, *, batch, heads, sq, skv, scale, lse=None):
     _store(out, o.transpose(1, 2).reshape(batch * sq, D))
     if lse is not None:
         _store(lse, torch.logsumexp(s, -1))
+
+
+def pick_kv_split(units, key_blocks, max_split=8):
+    from fast3r_b200.ops import pick_kv_split as f
+    return f(units, key_blocks, max_split)
+
+
+def attention_partial(q, kv, part_o, part_lse, *, part_base, n_split, batch, heads, sq, kv_rows_total, kv_row0, skv,
+                      scale):
+    D = heads * 64
+    qh = q.reshape(batch, sq, heads, 64).transpose(1, 2).float()
+    kvb = kv.reshape(batch, kv_rows_total, -1)[:, kv_row0:kv_row0 + skv]
+    nblk = (skv + 127) // 128
+    for s_ in range(n_split):
+        lo, hi = (s_ * nblk // n_split) * 128, min(((s_ + 1) * nblk // n_split) * 128, skv)
+        kh = kvb[:, lo:hi, :D].reshape(batch, hi - lo, heads, 64).transpose(1, 2).float()
+        vh = kvb[:, lo:hi, D:].reshape(batch, hi - lo, heads, 64).transpose(1, 2).float()
+        sc = (qh @ kh.transpose(-2, -1)) * scale
+        p_ = sc.softmax(-1).to(BF16).float()  # (the kernel rounds P to bf16)
+        part_o[part_base + s_] = (p_ @ vh).transpose(1, 2).reshape(batch * sq, D)
+        part_lse[part_base + s_] = torch.logsumexp(sc, -1)
+
+
+def attention_merge(part_o, part_lse, n_parts, out, *, batch, heads, sq):
+    lse = part_lse[:n_parts]                                  # (P, b, h, sq)
+    w = torch.exp(lse - lse.amax(0, keepdim=True))
+    w = (w / w.sum(0, keepdim=True)).permute(0, 1, 3, 2)      # (P, b, sq, h)
+    o = part_o[:n_parts].reshape(n_parts, batch, sq, heads, 64)
+    _store(out, (o * w[..., None]).sum(0).reshape(batch * sq, heads * 64))
 
 
 def layernorm(x, w, b, eps, out):

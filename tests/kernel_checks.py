@@ -178,6 +178,46 @@ def check_attention(batch=2, heads=2, sq=736, skv=736, scale=0.125, seed=90, qsc
     return e, 8e-3, info
 
 
+def check_attention_ranges(heads=2, sq=700, chunk=736, world=4, rank=1, scale=0.16019, seed=95):
+    """Sequence-parallel style: attend to the local key chunk, then to the ranges before / after it (each key-sliced),
+    merge by log-sum-exp; must equal attention over all keys."""
+    D = heads * 64
+    skv = chunk * world
+    q = _rand((sq, D), seed)
+    kv = _rand((skv, 2 * D), seed + 1)
+    lo, hi = rank * chunk, (rank + 1) * chunk
+    ranges = [(lo, chunk)] + [r for r in ((0, lo), (hi, skv - hi)) if r[1] > 0]
+    splits = [1, 2, 3][:len(ranges)]
+    slots = sum(splits)
+    part_o = torch.zeros(slots, sq, D, dtype=torch.float32, device="cuda")
+    part_lse = torch.zeros(slots, 1, heads, sq, dtype=torch.float32, device="cuda")
+    base = 0
+    for (row0, n), ns in zip(ranges, splits):
+        ops.attention_partial(q, kv, part_o, part_lse, part_base=base, n_split=ns, batch=1, heads=heads, sq=sq,
+                              kv_rows_total=skv, kv_row0=row0, skv=n, scale=scale)
+        base += ns
+    out = torch.zeros(sq, D, dtype=torch.bfloat16, device="cuda")
+    ops.attention_merge(part_o, part_lse, slots, out, batch=1, heads=heads, sq=sq)
+    qh = q.reshape(1, sq, heads, 64).transpose(1, 2)
+    kh = kv[:, :D].reshape(1, skv, heads, 64).transpose(1, 2)
+    vh = kv[:, D:].reshape(1, skv, heads, 64).transpose(1, 2)
+    ref = attention_ref(qh, kh, vh, scale).transpose(1, 2).reshape(sq, D)
+    return rel(out, ref), 8e-3, dict(nan=bool(torch.isnan(out.float()).any()))
+
+
+def check_attention_autosplit(batch=1, heads=4, sq=600, skv=4000, scale=0.16019, seed=97):
+    """Few query tiles: ops.attention slices the keys (pick_kv_split) and merges; same result as one slice."""
+    D = heads * 64
+    q = _rand((batch * sq, D), seed)
+    kv = _rand((batch * skv, 2 * D), seed + 1)
+    a = torch.zeros(batch * sq, D, dtype=torch.bfloat16, device="cuda")
+    b = torch.zeros_like(a)
+    ops.attention(q, kv, a, batch=batch, heads=heads, sq=sq, skv=skv, scale=scale, kv_split=1)
+    ns = ops.pick_kv_split(batch * heads * ((sq + 255) // 256), (skv + 127) // 128)
+    ops.attention(q, kv, b, batch=batch, heads=heads, sq=sq, skv=skv, scale=scale)
+    return rel(b, a), 3e-3, dict(auto_split=ns)
+
+
 def check_layernorm(rows=1000, dim=1024, eps=1e-5, seed=100):
     x = _rand((rows, dim), seed, 2.0, torch.float32) + 0.5
     w, b = _rand((dim,), seed + 1, 1.0, torch.float32), _rand((dim,), seed + 2, 1.0, torch.float32)
@@ -347,6 +387,9 @@ ALL = [
     ("attn_24", check_attention, dict(batch=3, heads=2, sq=24, skv=24)),
     ("attn_long_3072", check_attention, dict(batch=1, heads=2, sq=512, skv=3072, scale=0.16019)),
     ("attn_peaky", check_attention, dict(batch=1, heads=2, sq=512, skv=2048, scale=0.5, qscale=3.0)),
+    ("attn_ranges_merge", check_attention_ranges, {}),
+    ("attn_ranges_merge_rank0", check_attention_ranges, dict(rank=0, world=3, chunk=500, sq=300)),
+    ("attn_autosplit", check_attention_autosplit, {}),
     # the bench regime: 23 552 keys (N=32 views) = 184 key blocks of lazy-rescale accumulation, flat and peaky scores
     ("attn_skv23552", check_attention, dict(batch=1, heads=2, sq=512, skv=23552, scale=0.16019)),
     ("attn_skv23552_peaky", check_attention, dict(batch=1, heads=1, sq=256, skv=23552, scale=0.5, qscale=3.0)),

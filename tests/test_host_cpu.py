@@ -128,8 +128,15 @@ def _sp_worker(rank, world, port, n_views, batch, tok, C, ret):
     full = torch.arange(batch * n_views * tok * C, dtype=torch.float32).view(batch, n_views * tok, C)
     local = full[:, lo * tok:hi * tok].contiguous().view(-1, C)
     kvx = sp.make_kv_exchange(batch, (hi - lo) * tok, C // 2)
-    allkv, s_total = kvx(local)
-    ok = s_total == n_views * tok and torch.equal(allkv, full.reshape(-1, C))
+    seen = {}
+
+    class FakeOps:  # the general path hands the assembled K|V of ALL ranks to one attention call
+        @staticmethod
+        def attention(q, kv_all, att, *, batch, heads, sq, skv, scale):
+            seen.update(kv=kv_all, skv=skv, sq=sq, batch=batch)
+
+    kvx.attend(FakeOps, None, local, None, heads=1, scale=1.0, x3=False)
+    ok = seen["skv"] == n_views * tok and seen["sq"] == (hi - lo) * tok and torch.equal(seen["kv"], full.reshape(-1, C))
     # result gathering
     fr = [dict() for _ in range(n_views)]
     for i in range(lo, hi):

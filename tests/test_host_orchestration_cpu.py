@@ -137,6 +137,26 @@ def test_inference_dtype_selects_precision(emulated, golden_dir):
     assert err["32"] < PARITY_TOL < err[torch.bfloat16], err
 
 
+def test_emulated_partial_merge_equals_attention():
+    """Spec of f3r_attention_partial / f3r_attention_merge: key ranges attended separately and merged by log-sum-exp
+    equal the attention over all keys (what parallel.KVExchange relies on)."""
+    from tests import abi_emulator as E
+    heads, sq, chunk, world, rank = 2, 70, 90, 3, 1
+    D, skv = heads * 64, chunk * world
+    g = torch.Generator().manual_seed(3)
+    q, kv = torch.randn(sq, D, generator=g).bfloat16(), torch.randn(skv, 2 * D, generator=g).bfloat16()
+    lo, hi = rank * chunk, (rank + 1) * chunk
+    ranges, splits = [(lo, chunk), (0, lo), (hi, skv - hi)], [1, 1, 1]
+    part_o, part_lse = torch.zeros(3, sq, D), torch.zeros(3, 1, heads, sq)
+    for i, ((row0, n), ns) in enumerate(zip(ranges, splits)):
+        E.attention_partial(q, kv, part_o, part_lse, part_base=i, n_split=ns, batch=1, heads=heads, sq=sq,
+                            kv_rows_total=skv, kv_row0=row0, skv=n, scale=0.2)
+    out, ref = torch.zeros(sq, D).bfloat16(), torch.zeros(sq, D).bfloat16()
+    E.attention_merge(part_o, part_lse, 3, out, batch=1, heads=heads, sq=sq)
+    E.attention(q, kv, ref, batch=1, heads=heads, sq=sq, skv=skv, scale=0.2)
+    assert rel_l2(out.float(), ref.float()) < 6e-3
+
+
 # ------------------------------------------------------------------ sequence parallel over gloo (2 ranks, CPU)
 def _sp_worker(rank, world, port, tag, golden_dir, ret, seed_skew=0):
     import torch.distributed as dist

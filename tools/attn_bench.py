@@ -30,8 +30,9 @@ def main():
         out = torch.empty(b * sq, D, dtype=torch.bfloat16, device=dev)
         ref = None
         flops = 4.0 * b * sq * skv * D
-        for emu in range(6):
+        for split, emu in [(sp, e) for sp in (1, 2) for e in range(5)]:
             L.set_option("attn_emu", emu)
+            L.set_option("attn_split", split)
             ops.attention(q, kv, out, batch=b, heads=h, sq=sq, skv=skv, scale=scale)
             torch.cuda.synchronize()
             ts = []
@@ -45,15 +46,16 @@ def main():
                 ts.append(e0.elapsed_time(e1))
             ms = sorted(ts)[len(ts) // 2]
             o = out.float()
-            if emu == 0:
+            if emu == 0 and split == 1:
                 ref = o.clone()
                 err = 0.0
             else:
                 err = float((o - ref).norm() / ref.norm())
-            res[f"{name}/emu{emu}"] = dict(ms=ms, tflops=flops / ms / 1e9, rel_vs_emu0=err, nan=bool(torch.isnan(o).any()))
-            print(name, "emu", emu, f"{ms:.3f} ms  {flops / ms / 1e9:.0f} TFLOP/s  rel vs emu0 {err:.2e}", flush=True)
+            res[f"{name}/split{split}/emu{emu}"] = dict(ms=ms, tflops=flops / ms / 1e9, rel_vs_emu0=err, nan=bool(torch.isnan(o).any()))
+            print(name, "split", split, "emu", emu, f"{ms:.3f} ms  {flops / ms / 1e9:.0f} TFLOP/s  rel vs emu0 {err:.2e}", flush=True)
         del q, kv, out, ref
     L.set_option("attn_emu", -1)
+    L.set_option("attn_split", -1)
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump(res, open("gpurun_out/attn_bench.json", "w"), indent=1)
 
