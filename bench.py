@@ -68,7 +68,12 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def mark(self):
+        """Start of the timed region: samples taken before this call are dropped (nvidia-smi needs ~1 s to come up, so
+        the sampler is started ahead of the region)."""
+        self.t0 = time.time()
 
     def stop(self):
         if self.proc is None:
@@ -79,7 +84,10 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
-        for ln in self.lines:
+        t0 = getattr(self, "t0", 0.0)
+        for ts, ln in self.lines:
+            if ts < t0:
+                continue
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -400,14 +408,40 @@ def run_ours(args, rank, world, local_rank):
     views_dev = make_views(N, device=dev, only=rng)
     views_host = make_views(N, pinned=True, only=rng)
     sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         torch.manual_seed(7)
         model(views_dev)
-    if rank == 0:
-        sampler.start()
+    torch.cuda.synchronize()
+    sampler.mark()
+    if sp is not None:
+        sp.timers = []
     ms, launches, timer = timed_device(views_dev, args.steps, 0)
     clocks = sampler.stop() if rank == 0 else None
     roof, att_ms = attention_roofline(timer, N, ms, clocks, peak_tf, peak_src)
+    sp_trace = None
+    if sp is not None and sp.timers:
+        tr = sp.timers
+        sp.timers = None
+        n = len(tr)
+        avg = lambda f: sum(f(e) for e in tr) / n  # noqa: E731
+        sp_trace = {"calls": n,
+                    "attend_total_ms": avg(lambda e: e[0].elapsed_time(e[3])),
+                    "local_chunk_attention_ms": avg(lambda e: e[0].elapsed_time(e[1])),
+                    "remote_chunks_attention_incl_wait_ms": avg(lambda e: e[1].elapsed_time(e[2])),
+                    "merge_ms": avg(lambda e: e[2].elapsed_time(e[3])),
+                    "allgather_on_comm_stream_ms": avg(lambda e: e[4].elapsed_time(e[5])),
+                    "allgather_end_after_local_end_ms": avg(lambda e: e[1].elapsed_time(e[5]))}
+        att_ms = sp_trace["attend_total_ms"]
+        sq = (rng[1] - rng[0]) * P_TOK
+        flops = 4.0 * sq * (N * P_TOK) * DMODEL
+        ach = flops / (att_ms * 1e-3) / 1e12
+        roof = {"kernel": "attention_kernel key-range partials + merge incl. exposed K|V exchange wait "
+                          "(fusion decoder global attention, 24 per step)", "bound": "tensor", "achieved": ach,
+                "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "peak_source": peak_src,
+                "ms_per_launch": att_ms, "flops_per_launch": flops, "traffic": None,
+                "share_of_step": DEPTH * att_ms / ms}
 
     # ---- end to end through inference() (pinned host -> device -> host)
     def step_e2e():
@@ -435,6 +469,8 @@ def run_ours(args, rank, world, local_rank):
         roof.update(achieved=ach, frac=ach / peak_tf, ms_per_launch=att_ms_max, share_of_step=DEPTH * att_ms_max / ms)
 
     extra = {}
+    if sp_trace is not None:
+        extra["sp_attention_trace_rank0"] = sp_trace
     # ================= sharded vs un-sharded parity of THIS run (world > 1) =================
     if world > 1:
         torch.manual_seed(7)

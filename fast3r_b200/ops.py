@@ -141,12 +141,13 @@ NUM_SMS = 148
 
 def pick_kv_split(units: int, key_blocks: int, max_split: int = 8) -> int:
     """Key slices per (batch, head, 256-row query tile) unit so that units * slices CTAs fill whole waves of the 148
-    SMs (one CTA per SM): minimises ceil(units*s / 148) / s; every slice keeps >= 4 key blocks; 1 = no slicing."""
+    SMs (one CTA per SM): minimises ceil(units*s / 148) / s; every slice keeps >= 16 key blocks (below that the extra
+    prologues and the merge pass cost more than the idle SMs, measured at N=4); 1 = no slicing."""
     if units >= 3 * NUM_SMS:
         return 1
     best, best_cost = 1, None
     for s_ in range(1, max_split + 1):
-        if s_ > 1 and key_blocks // s_ < 4:
+        if s_ > 1 and key_blocks // s_ < 16:
             break
         cost = -(-units * s_ // NUM_SMS) / s_ * (1.0 + 0.01 * (s_ - 1))  # (+1 % per extra slice: merge + prologues)
         if best_cost is None or cost < best_cost - 1e-9:

@@ -94,9 +94,17 @@ class KVExchange:
         if kv.data_ptr() != slot.data_ptr():
             slot.copy_(kv)
         compute = torch.cuda.current_stream(kv.device)
+        tm = sp.timers  # optional CUDA-event trace of the phases (bench.py): list of per-call event tuples
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)] if tm is not None else None
+        if ev:
+            ev[0].record(compute)
         self.comm_stream.wait_stream(compute)  # K|V of this layer is complete; previous layer's readers are done
         with torch.cuda.stream(self.comm_stream):
+            if ev:
+                ev[4].record(self.comm_stream)
             dist.all_gather_into_tensor(self.buf.view(-1, C), slot, group=sp.group)
+            if ev:
+                ev[5].record(self.comm_stream)
         sp.bytes_exchanged += self.buf.numel() * self.buf.element_size()
         S, sl = self.s_total, self.s_local
         lo, hi = sp.rank * sl, (sp.rank + 1) * sl
@@ -112,13 +120,20 @@ class KVExchange:
         base = 0
         for i, ((row0, n), ns) in enumerate(zip(ranges, splits)):
             if i == 1:
+                if ev:
+                    ev[1].record(compute)
                 compute.wait_stream(self.comm_stream)  # the other ranks' keys have landed
             ops.attention_partial(q, kv_all, part_o, part_lse, part_base=base, n_split=ns, batch=1, heads=heads, sq=sl,
                                   kv_rows_total=S, kv_row0=row0, skv=n, scale=scale)
             base += ns
         if len(ranges) == 1:
             compute.wait_stream(self.comm_stream)
+        if ev:
+            ev[2].record(compute)
         ops.attention_merge(part_o, part_lse, slots, att, batch=1, heads=heads, sq=sl)
+        if ev:
+            ev[3].record(compute)
+            tm.append(ev)
 
 
 class SequenceParallel:
@@ -130,6 +145,7 @@ class SequenceParallel:
         self.world = dist.get_world_size(group)
         self.gather_preds = gather_preds
         self.overlap = True   # False: always all-gather first, then one attention call (A/B measurements)
+        self.timers = None    # set to a list to collect CUDA-event traces of KVExchange.attend (bench.py)
         self._ranges = None
         self.bytes_exchanged = 0
 

@@ -1,8 +1,10 @@
 #!/bin/bash
-# usage: tools/gpurun_retry.sh <timeout-seconds> '<command>'   (retries while the pod answers busy / no box: rc 3)
+# usage: [GPUS=N] tools/gpurun_retry.sh <timeout-seconds> '<command>'   (retries while the pod answers busy / no box: rc 3)
 T=$1; shift
+EXTRA=""
+if [ -n "$GPUS" ]; then EXTRA="--gpus $GPUS"; fi
 for i in $(seq 1 30); do
-  /usr/local/graft/bin/gpurun --timeout "$T" -- "$@"
+  /usr/local/graft/bin/gpurun $EXTRA --timeout "$T" -- "$@"
   rc=$?
   if [ $rc -ne 3 ]; then exit $rc; fi
   sleep 90

@@ -36,10 +36,26 @@ for (n_views, batch, H, W) in [(5, 1, 64, 96), (4, 2, 48, 64), (2 * world, 1, 96
     print(f"  rank {rank}: worst {worst:.3e}", flush=True)
     t = torch.tensor([worst], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    fast = batch == 1 and n_views % world == 0   # overlapped exchange: key-range partials merged in fp32
     if rank == 0:
         print(f"views={n_views} batch={batch} {H}x{W}: max rel diff vs single GPU = {t.item():.3e}, "
-              f"KV bytes exchanged/rank = {sp.bytes_exchanged}")
-    ok = ok and t.item() < 1e-5
+              f"KV bytes exchanged/rank = {sp.bytes_exchanged}, path = {'overlapped partials' if fast else 'all-gather'}")
+    if not fast:
+        ok = ok and t.item() < 1e-5      # same kernels, same key order: bit-identical
+    else:
+        # different (but equally valid) bf16 rounding points: judge both against the fp32 oracle on the same inputs
+        from oracle import fast3r_oracle as O
+        enc, dec, head = tiny_args()
+        torch.manual_seed(7)
+        gold = O.forward(synth_state_dict(shapes, seed=0), enc, dec, head, synth_images(n_views, batch, H, W))
+        rl2 = lambda x, y: float((x.double() - y.double()).norm() / y.double().norm())  # noqa: E731
+        e_sp = max(rl2(torch.cat([p[k].float().cpu().flatten() for p in out]), torch.cat([p[k].flatten() for p in gold]))
+                   for k in gold[0])
+        e_1 = max(rl2(torch.cat([p[k].float().cpu().flatten() for p in ref]), torch.cat([p[k].flatten() for p in gold]))
+                  for k in gold[0])
+        if rank == 0:
+            print(f"   rel-L2 vs fp32 oracle: sharded {e_sp:.3e}, single GPU {e_1:.3e}")
+        ok = ok and e_sp < 1.3e-2 and e_sp < 1.5 * e_1 + 1e-3
 dist.barrier()
 if rank == 0:
     print("SP_PARITY_OK" if ok else "SP_PARITY_FAIL")
