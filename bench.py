@@ -493,8 +493,16 @@ def run_ours(args, rank, world, local_rank):
     def extra_config(n_views, steps=2, warmup=1):
         r = shard_views(n_views, world)[rank] if world > 1 else None
         vd = make_views(n_views, device=dev, only=r)
+        if sp is not None:
+            sp.timers = []
         m, _l, tm = timed_device(vd, steps, warmup)
         rf, am = attention_roofline(tm, n_views, m, clocks, peak_tf, peak_src)
+        if sp is not None and sp.timers:   # sharded: the attention of a layer = key-range partials + merge (+ exposed wait)
+            tr, sp.timers = sp.timers[-DEPTH * steps:], None
+            am = sum(e[0].elapsed_time(e[3]) for e in tr) / len(tr)
+            fl = 4.0 * (r[1] - r[0]) * P_TOK * (n_views * P_TOK) * DMODEL
+            rf = {"kernel": "attention_kernel key-range partials + merge incl. exposed K|V exchange wait", "bound": "tensor",
+                  "peak": peak_tf, "unit": "TFLOP/s", "peak_source": peak_src, "flops_per_launch": fl, "traffic": None}
         m, am = allmax([m, am])
         if rf is not None:
             a = rf["flops_per_launch"] / (am * 1e-3) / 1e12
