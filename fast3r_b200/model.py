@@ -24,7 +24,25 @@ import torch.nn as nn
 from . import lib as L
 from . import ops
 
+try:  # same hub integration as the reference (fast3r/models/fast3r.py:45-49): from_pretrained / save_pretrained
+    from huggingface_hub import PyTorchModelHubMixin as _HubMixin
+except Exception:  # pragma: no cover - huggingface_hub is optional for the kernels themselves
+    class _HubMixin:  # type: ignore
+        def __init_subclass__(cls, **kw):
+            super().__init_subclass__()
+
 BF16, F32 = torch.bfloat16, torch.float32
+
+
+def _plain(cfg):
+    """Plain python containers out of any Mapping / Sequence config (omegaconf DictConfig / ListConfig included), the
+    job of OmegaConf.to_container in the reference ctor (fast3r/models/fast3r.py:59-66) without importing omegaconf."""
+    from collections.abc import Mapping, Sequence
+    if isinstance(cfg, Mapping):
+        return {str(k): _plain(v) for k, v in cfg.items()}
+    if isinstance(cfg, Sequence) and not isinstance(cfg, (str, bytes)):
+        return [_plain(v) for v in cfg]
+    return cfg
 
 
 # --------------------------------------------------------------------------- parameter containers
@@ -258,8 +276,9 @@ def _require_cuda(device) -> None:
 PRECISIONS = ("bf16", "fp32")
 
 
-class Fast3R(nn.Module):
-    """Drop-in replacement for fast3r.models.fast3r.Fast3R (same ctor / state_dict / forward contract).
+class Fast3R(nn.Module, _HubMixin, repo_url="https://github.com/facebookresearch/fast3r", tags=["image-to-3d"]):
+    """Drop-in replacement for fast3r.models.fast3r.Fast3R (same ctor / state_dict / forward contract, same
+    huggingface_hub mixin: ``Fast3R.from_pretrained(dir_or_repo)`` / ``save_pretrained``).
 
     ``precision`` selects the numeric path of the kernels:
       * ``"bf16"`` (default, the benchmarked path): bf16 tensor-core operands, fp32 accumulation / residual stream /
@@ -270,9 +289,9 @@ class Fast3R(nn.Module):
 
     def __init__(self, encoder_args: dict, decoder_args: dict, head_args: dict, freeze="none"):
         super().__init__()
-        self.encoder_args = dict(encoder_args)
-        self.decoder_args = dict(decoder_args)
-        self.head_args = dict(head_args)
+        self.encoder_args = _plain(encoder_args)
+        self.decoder_args = _plain(decoder_args)
+        self.head_args = _plain(head_args)
         self.build_encoder(self.encoder_args)
         self.build_decoder(self.decoder_args)
         self.build_head(self.head_args)
@@ -349,6 +368,31 @@ class Fast3R(nn.Module):
         r = super().load_state_dict(ckpt, **kw)
         self._packed, self._packed_sig = {}, {}
         return r
+
+    def load_from_dust3r_checkpoint(self, dust3r_checkpoint_path: str):
+        """Behaviour of fast3r/models/fast3r.py:162-239: take patch_embed / enc_blocks / enc_norm (-> encoder.*) and
+        downstream_head1 (-> downstream_head.*) from a DUSt3R checkpoint; a head that does not fit leaves the current head
+        untouched (and ``head_args['skip_load_pretrained_head']`` skips it).  Returns (loaded, not_loaded) key sets."""
+        ckpt = torch.load(dust3r_checkpoint_path, weights_only=False)["model"]
+        enc_sd, head_sd = {}, {}
+        for key, value in ckpt.items():
+            if key.startswith(("patch_embed", "enc_blocks", "enc_norm")):
+                enc_sd["encoder." + key] = value
+            elif key.startswith("downstream_head1"):
+                head_sd[key.replace("downstream_head1", "downstream_head", 1)] = value
+        loaded = set()
+        res = self.load_state_dict(enc_sd, strict=False)
+        loaded |= {k[len("encoder."):] for k in enc_sd if k not in set(res.unexpected_keys)}
+        if not self.head_args.get("skip_load_pretrained_head", False):
+            keep = {k: v.clone() for k, v in self.downstream_head.state_dict().items()}
+            try:
+                res = self.load_state_dict(head_sd, strict=False)
+                loaded |= {k.replace("downstream_head", "downstream_head1", 1) for k in head_sd
+                           if k not in set(res.unexpected_keys)}
+            except RuntimeError:
+                self.downstream_head.load_state_dict(keep)
+        self._packed, self._packed_sig = {}, {}
+        return loaded, set(ckpt.keys()) - loaded
 
     def _tap(self, name, t):
         if self._taps is not None and name not in self._taps:  # first writer wins (global head before local head)
@@ -698,6 +742,53 @@ class Fast3R(nn.Module):
             return final_results, profiling_info
         return final_results
 
+    # ---- portrait views (ManyAR_PatchEmbed + landscape_only heads: fast3r/dust3r/patch_embed.py:59-105,
+    #      fast3r/dust3r/utils/misc.py:74-104)
+    def _portrait_flags(self, views, H, W):
+        """Per view: True if it is a portrait image stored transposed in a landscape buffer (true_shape = (W, H)).  The
+        reference supports that only with patch_embed_cls="ManyAR_PatchEmbed" and head landscape_only=True (training
+        configuration); with PatchEmbedDust3R / landscape_only=False (what every inference caller uses) true_shape has to
+        equal the stored shape (misc.py:67-72 takes the head resolution from it)."""
+        flags = []
+        many_ar = self.encoder.patch_embed_cls == "ManyAR_PatchEmbed" and self.landscape_only
+        for v in views:
+            ts = v.get("true_shape", None)
+            if ts is None:
+                flags.append(False)
+                continue
+            ts = torch.as_tensor(ts).reshape(-1, 2)
+            same = bool(((ts[:, 0] == H) & (ts[:, 1] == W)).all())
+            swapped = bool(((ts[:, 0] == W) & (ts[:, 1] == H)).all()) and H != W
+            if same:
+                flags.append(False)
+            elif swapped and many_ar:
+                flags.append(True)
+            elif swapped:
+                raise ValueError("portrait true_shape needs patch_embed_cls='ManyAR_PatchEmbed' and landscape_only=True "
+                                 "(with PatchEmbedDust3R / landscape_only=False true_shape must equal the image shape)")
+            else:
+                raise NotImplementedError("fast3r_b200: true_shape must be the image shape or its transpose, identical for "
+                                          "all batch elements of a view")
+        return flags
+
+    def _forward_portrait(self, views, portrait, profiling):
+        """Portrait views are un-transposed (a strided view of the same pixels), go through the shape-grouped path in their
+        true geometry - patch grid, RoPE positions and DPT head at (W, H) - and their predictions are transposed back to
+        the landscape storage layout, exactly what ManyAR_PatchEmbed + transpose_to_landscape.wrapper_yes compute."""
+        vs = []
+        for v, p in zip(views, portrait):
+            if p:
+                v = dict(v)
+                v["img"] = v["img"].swapaxes(-1, -2)
+            vs.append(v)
+        out = self._forward_mixed(vs, profiling)
+        res, info = out if profiling else (out, None)
+        for r, p in zip(res, portrait):
+            if p:
+                for k in list(r):
+                    r[k] = r[k].swapaxes(1, 2)
+        return (res, info) if profiling else res
+
     # ---- forward (fast3r/models/fast3r.py:302-497)
     def forward(self, views, profiling=False):
         if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
@@ -727,13 +818,9 @@ class Fast3R(nn.Module):
         ps = self.encoder.patch_size
         if H % ps or W % ps:
             raise AssertionError(f"Input image size ({H}x{W}) is not a multiple of patch size ({ps}).")
-        for v in views:
-            ts = v.get("true_shape", None)
-            if ts is not None:
-                ts = torch.as_tensor(ts)
-                if not bool(((ts[..., 0] == H) & (ts[..., 1] == W)).all()):
-                    raise NotImplementedError("fast3r_b200: true_shape must equal the image shape "
-                                              "(portrait transposition of ManyAR_PatchEmbed is not built)")
+        portrait = self._portrait_flags(views, H, W)
+        if any(portrait):
+            return self._forward_portrait(views, portrait, profiling)
         sp = self.sp_group
         if sp is None:
             lo, hi = 0, N

@@ -49,7 +49,7 @@ def import_reference():
 
     if "fast3r.utils" not in sys.modules or not hasattr(sys.modules["fast3r.utils"], "pylogger"):
         fu = types.ModuleType("fast3r.utils")
-        fu.__path__ = []
+        fu.__path__ = [os.path.join(REFERENCE_ROOT, "fast3r", "utils")]  # real submodules, but not the hydra-laden __init__
         pl = types.ModuleType("fast3r.utils.pylogger")
 
         class RankedLogger(logging.LoggerAdapter):

@@ -154,6 +154,32 @@ def run_blocks():
     print("vitl_blocks saved", os.path.getsize(os.path.join(HERE, "vitl_blocks.pt")) / 1e6, "MB")
 
 
+def run_tiny_portrait(tag="tiny_portrait"):
+    """Training-style configuration: ManyAR_PatchEmbed + landscape_only=True heads; view 1 is a PORTRAIT image stored
+    transposed in the landscape buffer (true_shape = (W, H)) - fast3r/dust3r/patch_embed.py:59-105,
+    fast3r/dust3r/utils/misc.py:74-104."""
+    enc, dec, head = tiny_args()
+    enc.update(patch_embed_cls="ManyAR_PatchEmbed")
+    head.update(landscape_only=True)
+    torch.manual_seed(0)
+    model = Fast3R(dict(enc), dict(dec), dict(head)).eval()
+    shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    model.load_state_dict(synth_state_dict(shapes, seed=0))
+    B, N, H, W = 1, 3, 64, 96
+    imgs = synth_images(N, B, H, W)
+    true_shapes = [(H, W), (W, H), (H, W)]
+    views = [dict(img=imgs[i], true_shape=torch.tensor([true_shapes[i]] * B, dtype=torch.int32), idx=i, instance=str(i),
+                  dataset="synthetic", label=f"v{i}") for i in range(N)]
+    torch.manual_seed(7)
+    with torch.no_grad():
+        preds = model(views)
+    out = dict(shapes=shapes, B=B, N=N, H=H, W=W, true_shapes=true_shapes, weight_seed=0, rng_seed=7,
+               enc_over=dict(patch_embed_cls="ManyAR_PatchEmbed"), head_over=dict(landscape_only=True),
+               preds=[{k: half(v) for k, v in p.items()} for p in preds])
+    torch.save(out, os.path.join(HERE, f"{tag}.pt"))
+    print(tag, "saved", os.path.getsize(os.path.join(HERE, f"{tag}.pt")) / 1e6, "MB", {k: tuple(v.shape) for k, v in preds[1].items()})
+
+
 def run_vitl_n4(tag="vitl_n4_368x512", stride=4):
     """BASELINE.json configs[0]: full ViT-L/512 (24+24 layers, 2 DPT heads), N=4 views 512x368, fp32 on CPU through the
     reference's own inference(..., dtype="32").  The full-resolution preds are 24 MB, so the fixture keeps every
@@ -195,6 +221,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "vitl_n4":
         run_vitl_n4()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "portrait":
+        run_tiny_portrait()
+        sys.exit(0)
     run_tiny(1, 3, 64, 96, "tiny_b1_n3")
     run_tiny(2, 2, 48, 64, "tiny_b2_n2")
     # configuration quirks the replacement must honour
@@ -205,4 +234,5 @@ if __name__ == "__main__":
     run_tiny_mixed()
     run_tiny(1, 3, 32, 48, "tiny_trainmode", train_mode=True)
     run_blocks()
+    run_tiny_portrait()
     run_vitl_n4()

@@ -226,3 +226,28 @@ def test_vitl_two_views_vs_oracle():
     print("vitl", rep)
     for k, v in rep.items():
         assert v <= 1e-2, rep
+
+
+@pytest.mark.parametrize("precision,tol", [("bf16", BF16_TOL), ("fp32", PARITY_TOL)])
+def test_portrait_view_vs_reference_golden(golden_dir, precision, tol):
+    """ManyAR_PatchEmbed + landscape_only heads, one portrait view stored transposed (fast3r/dust3r/patch_embed.py:59-105,
+    fast3r/dust3r/utils/misc.py:74-104) against the reference's outputs."""
+    from fast3r_b200 import Fast3R, tiny_args
+    g = torch.load(os.path.join(golden_dir, "tiny_portrait.pt"))
+    enc, dec, head = tiny_args()
+    enc.update(g["enc_over"]); head.update(g["head_over"])
+    model = Fast3R(enc, dec, head).eval().set_precision(precision)
+    model.load_state_dict(synth_state_dict(g["shapes"], seed=g["weight_seed"]))
+    model = model.cuda()
+    imgs = synth_images(g["N"], g["B"], g["H"], g["W"])
+    views = [dict(img=im.cuda(), true_shape=torch.tensor([g["true_shapes"][i]] * g["B"], dtype=torch.int32))
+             for i, im in enumerate(imgs)]
+    torch.manual_seed(g["rng_seed"])
+    preds = model(views)
+    rep = {k: rel_l2(torch.cat([p[k].float().cpu().flatten() for p in preds]),
+                     torch.cat([q[k].flatten() for q in g["preds"]])) for k in g["preds"][0]}
+    print("portrait", precision, rep)
+    for p, q in zip(preds, g["preds"]):
+        for k in q:
+            assert p[k].shape == q[k].shape
+    assert all(v <= tol for v in rep.values()), rep
