@@ -203,6 +203,20 @@ int f3r_gemm(const f3r_gemm_desc* d, void* stream) {
       if (make_tmap(&to0b, d->out0b, 4, dims, str, box, dt, sw)) return 1;
     }
   }
+  a.k_split = 1;
+  static int ksplit_pref = -1;  // F3R_GEMM_KSPLIT=1 disables the K slicing (A/B measurements)
+  if (ksplit_pref < 0) { const char* e = getenv("F3R_GEMM_KSPLIT"); ksplit_pref = (e && e[0] == '1') ? 1 : 0; }
+  if (a.tma_epi == 2 && d->taps == 1 && ksplit_pref != 1) {
+    // x += A W^T with fewer output tiles than SM (pairs): cut K into slices, each CTA reduce-adds its partial sum
+    const long slots = num_sms() / cluster;
+    const long items = static_cast<long>((a.num_m_tiles + cluster - 1) / cluster) * a.num_n_tiles;
+    const int k_iters = (d->k + 63) / 64;
+    double best = 1e30;
+    for (int s = 1; s <= 4 && (s == 1 || k_iters / s >= 16); ++s) {  // (short K: the reduce-add epilogue dominates, slicing loses)
+      const double cost = static_cast<double>((items * s + slots - 1) / slots) / s * (1.0 + 0.03 * (s - 1));
+      if (cost < best - 1e-9) { best = cost; a.k_split = s; }
+    }
+  }
   g_launches++;
   return check(f3r::launch_gemm(block_n, cluster, ta, tb, to0, to0b, a, num_sms(), static_cast<cudaStream_t>(stream)),
                "f3r_gemm");

@@ -21,6 +21,7 @@ struct GemmArgs {
   int ct_k, ct_cout;                   // EPI_CONVT
   int tma_epi;                         // 0: generic epilogue, 1: TMA store of out0(/out0b), 2: TMA reduce-add into fp32 out0
   int sbx_log2;                        // TMA-store box = (32 ch, sbx, 32/sbx) pixels, sbx = min(bw, 32)
+  int k_split;                         // K slices per output tile (>1 only with tma_epi == 2: partial sums reduce-added)
   int debug;                           // F3R_GEMM_DEBUG bitmask (1: no epilogue stores) - timing experiments only
   const float* bias;
   const void* res0;

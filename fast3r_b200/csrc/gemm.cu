@@ -111,8 +111,8 @@ __device__ __forceinline__ void gelu_fast2(float& x0, float& x1) {
 // Row-domain part: bias, RoPE, image-index embedding, or the FINAL 128->4 dot product.  Returns false if the chunk is
 // fully consumed here (FINAL).
 __device__ __forceinline__ bool epilogue_rows(const GemmArgs& p, float (&v)[32], int m, int col0, bool row_ok,
-                                              float (&fin)[4]) {
-  if (p.bias != nullptr) {
+                                              float (&fin)[4], bool add_bias) {
+  if (p.bias != nullptr && add_bias) {
     const float4* b4 = reinterpret_cast<const float4*>(p.bias + (p.epi == EPI_CONVT ? (col0 % p.ct_cout) : col0));
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -309,7 +309,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   const int cta_rank = kCluster > 1 ? static_cast<int>(cluster_ctarank()) : 0;
   const int first_item = kCluster > 1 ? static_cast<int>(cluster_id_x()) : static_cast<int>(blockIdx.x);
   const int item_stride = kCluster > 1 ? static_cast<int>(num_clusters_x()) : static_cast<int>(gridDim.x);
-  const int num_tiles = ((p.num_m_tiles + kCluster - 1) / kCluster) * p.num_n_tiles;
+  // split-K (only with the fp32 reduce-add epilogue, x += A W^T: partial sums of the K slices are added by the memory
+  // system): work item = (tile, K slice); used when there are fewer tiles than SMs (small M in sequence-parallel runs)
+  const int num_out_tiles = ((p.num_m_tiles + kCluster - 1) / kCluster) * p.num_n_tiles;
+  const int num_tiles = num_out_tiles * p.k_split;
   constexpr uint16_t kMask = (1u << kCluster) - 1;
   const int k_chunks = (p.K + BLOCK_K - 1) / BLOCK_K;
   const int k_iters = p.taps * k_chunks;
@@ -320,11 +323,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     if (lane == 0) {
       // ===================== TMA producer =====================
       int stage = 0; uint32_t phase = 0;
-      for (int tile = first_item; tile < num_tiles; tile += item_stride) {
+      for (int item = first_item; item < num_tiles; item += item_stride) {
+        const int tile = item % num_out_tiles, ks = item / num_out_tiles;
+        const int it0 = ks * k_iters / p.k_split, it1 = (ks + 1) * k_iters / p.k_split;
         const int mt = (tile / p.num_n_tiles) * kCluster + cta_rank, nt = tile % p.num_n_tiles;
         const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, img = mt / (p.tiles_x * p.tiles_y);
         const int x0 = tx * p.bw, y0 = ty * p.bh, n0 = nt * BLOCK_N;
-        for (int it = 0; it < k_iters; ++it) {
+        for (int it = it0; it < it1; ++it) {
           const int tap = it / k_chunks, kc = it % k_chunks;
           int dy = 0, dx = 0;
           if (p.taps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
@@ -348,11 +353,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, 0, 0);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int tile = first_item; tile < num_tiles; tile += item_stride) {
+      for (int item = first_item; item < num_tiles; item += item_stride) {
+        const int ks = item / num_out_tiles;
+        const int it0 = ks * k_iters / p.k_split, it1 = (ks + 1) * k_iters / p.k_split;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-        for (int it = 0; it < k_iters; ++it) {
+        for (int it = it0; it < it1; ++it) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint64_t a_desc = make_smem_desc_sw128(smem_u32(smem_a + stage * Cfg::kABytes), 1);
@@ -360,7 +367,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 #pragma unroll
           for (int k = 0; k < BLOCK_K / 16; ++k) {
             // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (addr >> 4) field
-            umma_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            umma_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (it > it0 || k > 0) ? 1u : 0u);
           }
           // frees the smem stage (in every CTA that multicasts into it) once the MMAs above have read it
           if constexpr (kCluster == 1) umma_commit(&empty_bar[stage]);
@@ -381,7 +388,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     const int r = quarter * 32 + lane;       // row inside the 128-row tile
     constexpr int kChunks = BLOCK_N / 32;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = first_item; tile < num_tiles; tile += item_stride) {
+    for (int item = first_item; item < num_tiles; item += item_stride) {
+      const int tile = item % num_out_tiles;
+      const bool add_bias = item < num_out_tiles;  // K slice 0 carries the bias
       const int mt = (tile / p.num_n_tiles) * kCluster + cta_rank, nt = tile % p.num_n_tiles;
       const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, img = mt / (p.tiles_x * p.tiles_y);
       const int px = tx * p.bw + r % p.bw, py = ty * p.bh + r / p.bw;
@@ -413,7 +422,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
-        if (epilogue_rows(p, v, m, col0, row_ok, fin) && !(p.debug & 1)) {
+        if (epilogue_rows(p, v, m, col0, row_ok, fin, add_bias) && !(p.debug & 1)) {
           if (p.tma_epi) {
             const bool to_b = p.split_col > 0 && col0 >= p.split_col;
             const int r0 = quarter * 32;  // first tile row of this warp
@@ -463,14 +472,12 @@ template <int BLOCK_N, int kCluster>
 static cudaError_t launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to0,
                                  const CUtensorMap& to0b, const GemmArgs& a, int num_sms, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  {  // (per launch: the attribute is per device and one process may drive several GPUs)
     cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BLOCK_N, kCluster>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
-  const int items = ((a.num_m_tiles + kCluster - 1) / kCluster) * a.num_n_tiles;
+  const int items = ((a.num_m_tiles + kCluster - 1) / kCluster) * a.num_n_tiles * a.k_split;
   const int max_clusters = num_sms / kCluster;
   const int clusters = items < max_clusters ? items : max_clusters;
   cudaLaunchConfig_t cfg = {};
