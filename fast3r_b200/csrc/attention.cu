@@ -87,7 +87,7 @@ F3R_DEVICE void exp2_emu2(float& e0, float& e1, float x0, float x1) {
 // kEmu of every 8 score pairs take the FMA-pipe exp2 (0: all on MUFU).  Spread patterns keep each group of four
 // consecutive pairs mixed so that the scheduler can interleave the two instruction streams.
 template <int kEmu> __host__ __device__ constexpr uint32_t emu_mask() {
-  return kEmu == 0 ? 0x00u : kEmu == 1 ? 0x10u : kEmu == 2 ? 0x44u : kEmu == 3 ? 0x92u : kEmu == 4 ? 0xAAu : 0xDAu;
+  return kEmu == 0 ? 0x00u : kEmu == 1 ? 0x10u : kEmu == 2 ? 0x44u : 0x92u;
 }
 
 template <int kEmu, int kSplit>
@@ -420,7 +420,7 @@ cudaError_t launch_attention(const CUtensorMap& tq, const CUtensorMap& tkv, cons
   // (or f3r_set_option) override the defaults for A/B measurements
   if (g_attn_emu < 0) {
     const char* e = getenv("F3R_ATTN_EMU");
-    g_attn_emu = (e && e[0] >= '0' && e[0] <= '5') ? (e[0] - '0') : F3R_ATT_EMU_DEFAULT;
+    g_attn_emu = (e && e[0] >= '0' && e[0] <= '3') ? (e[0] - '0') : F3R_ATT_EMU_DEFAULT;
   }
   if (g_attn_split < 0) {
     const char* e = getenv("F3R_ATTN_SPLIT");
@@ -430,7 +430,7 @@ cudaError_t launch_attention(const CUtensorMap& tq, const CUtensorMap& tkv, cons
   case E: return g_attn_split == 2 ? launch_attention_t<E, 2>(tq, tkv, a, stream)             \
                                    : launch_attention_t<E, 1>(tq, tkv, a, stream);
   switch (g_attn_emu) {
-    F3R_ATT_CASE(1) F3R_ATT_CASE(2) F3R_ATT_CASE(3) F3R_ATT_CASE(4) F3R_ATT_CASE(5)
+    F3R_ATT_CASE(1) F3R_ATT_CASE(2) F3R_ATT_CASE(3)
     default: return g_attn_split == 2 ? launch_attention_t<0, 2>(tq, tkv, a, stream)
                                       : launch_attention_t<0, 1>(tq, tkv, a, stream);
   }

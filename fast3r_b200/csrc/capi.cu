@@ -85,7 +85,7 @@ uint64_t f3r_launch_count(void) { return g_launches.load(); }
 int f3r_set_option(const char* name, int32_t value) {
   if (!name) return fail("f3r_set_option: null name");
   if (!strcmp(name, "attn_emu")) {
-    if (value < -1 || value > 5) return fail("f3r_set_option: attn_emu must be in [-1, 5]");
+    if (value < -1 || value > 3) return fail("f3r_set_option: attn_emu must be in [-1, 3]");
     f3r::g_attn_emu = value;
     return 0;
   }

@@ -77,7 +77,7 @@ size_t f3r_gemm_desc_size(void);
 uint64_t f3r_launch_count(void);
 
 /* Tuning knobs for A/B measurements (process-wide).  "attn_emu" = how many of every 8 exponential pairs of the
- * attention softmax are evaluated on the FMA pipe instead of MUFU.EX2 (0..5, -1 = built-in default); "attn_split" =
+ * attention softmax are evaluated on the FMA pipe instead of MUFU.EX2 (0..3, -1 = built-in default); "attn_split" =
  * softmax threads per query row (1 or 2, -1 = default). */
 int f3r_set_option(const char* name, int32_t value);
 

@@ -369,6 +369,7 @@ ALL = [
     ("linear_qkv_shape", check_linear, dict(M=2944, K=1024, N=3072)),
     ("linear_bn256", check_linear, dict(M=23552, K=256, N=1024)),
     ("linear_resid_gelu", check_linear_f32_residual_gelu, {}),
+    ("linear_resid_splitk", check_linear_f32_residual_gelu, dict(M=300, K=4096, N=256)),  # K slices reduce-added into x
     ("linear_split", check_linear_split, {}),
     ("rope_epilogue", check_rope, {}),
     ("idxemb_epilogue", check_idxemb, {}),

@@ -33,7 +33,7 @@ def main():
         out = torch.empty(b * sq, D, dtype=torch.bfloat16, device=dev)
         ref = None
         flops = 4.0 * b * sq * skv * D
-        for split, emu in [(1, 0), (1, 2), (2, 0), (2, 1), (2, 2)]:
+        for split, emu in [(1, 0), (1, 2), (1, 3), (2, 0), (2, 1), (2, 2)]:
             L.set_option("attn_emu", emu)
             L.set_option("attn_split", split)
             ops.attention(q, kv, out, batch=b, heads=h, sq=sq, skv=skv, scale=scale)
