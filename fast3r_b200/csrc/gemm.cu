@@ -111,7 +111,7 @@ __device__ __forceinline__ void gelu_fast2(float& x0, float& x1) {
 // Row-domain part: bias, RoPE, image-index embedding, or the FINAL 128->4 dot product.  Returns false if the chunk is
 // fully consumed here (FINAL).
 __device__ __forceinline__ bool epilogue_rows(const GemmArgs& p, float (&v)[32], int m, int col0, bool row_ok,
-                                              float (&fin)[4], bool add_bias) {
+                                              float (&fin)[4], bool add_bias, const float* w4s) {
   if (p.bias != nullptr && add_bias) {
     const float4* b4 = reinterpret_cast<const float4*>(p.bias + (p.epi == EPI_CONVT ? (col0 % p.ct_cout) : col0));
 #pragma unroll
@@ -150,13 +150,22 @@ __device__ __forceinline__ bool epilogue_rows(const GemmArgs& p, float (&v)[32],
     }
   }
   if (p.epi == EPI_FINAL) {
-    // ReLU -> conv1x1 (BLOCK_N -> 4), accumulated across the column chunks of this row
+    // ReLU -> conv1x1 (BLOCK_N -> 4), accumulated across the column chunks of this row.  The 4 x N weights sit in shared
+    // memory (all lanes read the same address: one broadcast 16-byte load per 4 weights instead of 4 global loads).
     if (row_ok) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float r = fmaxf(v[i], 0.f);
+      for (int o = 0; o < 4; ++o) {
+        const float4* w = reinterpret_cast<const float4*>(w4s + o * p.N + col0);
+        float acc = fin[o];
 #pragma unroll
-        for (int o = 0; o < 4; ++o) fin[o] = fmaf(r, __ldg(p.w4 + o * p.N + col0 + i), fin[o]);
+        for (int i = 0; i < 8; ++i) {
+          const float4 ww = w[i];
+          acc = fmaf(fmaxf(v[4 * i + 0], 0.f), ww.x, acc);
+          acc = fmaf(fmaxf(v[4 * i + 1], 0.f), ww.y, acc);
+          acc = fmaf(fmaxf(v[4 * i + 2], 0.f), ww.z, acc);
+          acc = fmaf(fmaxf(v[4 * i + 3], 0.f), ww.w, acc);
+        }
+        fin[o] = acc;
       }
     }
     return false;
@@ -287,6 +296,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   uint8_t* stage_base = smem + Cfg::kStages * Cfg::kStageBytes + 1024;  // 8 x 4 KB, 1024-aligned
   float* fin_smem = reinterpret_cast<float*>(stage_base);  // [2][128][4] (FINAL mode does not stage)
+  float* w4_smem = reinterpret_cast<float*>(stage_base + 4096);  // FINAL: [4][N <= 256] copy of the 1x1 conv weights
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -299,6 +309,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_ptr);
+  if (p.epi == EPI_FINAL)
+    for (int i = threadIdx.x; i < 4 * p.N; i += GEMM_THREADS) w4_smem[i] = __ldg(p.w4 + i);
   tc_fence_before();
   __syncthreads();
   if constexpr (kCluster > 1) cluster_sync_all();  // peer barriers are initialised before any multicast can arrive
@@ -422,7 +434,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
-        if (epilogue_rows(p, v, m, col0, row_ok, fin, add_bias) && !(p.debug & 1)) {
+        if (epilogue_rows(p, v, m, col0, row_ok, fin, add_bias, w4_smem) && !(p.debug & 1)) {
           if (p.tma_epi) {
             const bool to_b = p.split_col > 0 && col0 >= p.split_col;
             const int r0 = quarter * 32;  // first tile row of this warp
