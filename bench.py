@@ -328,6 +328,39 @@ def gemm_rates(dev, peak_tf):
     return out
 
 
+def ingest_rates(dev, hbm_gbs):
+    """resize + crop + normalise of load_images() for a 12-Mpixel photo (4032x3024 -> 512x384): the GPU kernels
+    (f3r_ingest_rgb8, bit-exact with Pillow) vs Pillow itself on one host core (what the reference's loop does per image)."""
+    import numpy as np
+    import torch
+    from PIL import Image
+    from fast3r_b200.ingest import ingest_rgb8
+    h, w = 3024, 4032
+    img = np.random.default_rng(0).integers(0, 256, (h, w, 3), dtype=np.uint8)
+    u8 = torch.from_numpy(img).to(dev)
+    out = torch.empty(3, 384, 512, dtype=torch.float32, device=dev)
+    for _ in range(3):
+        ingest_rgb8(u8, 512, out=out)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20):
+        ingest_rgb8(u8, 512, out=out)
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) / 20 * 1e3
+    pil = Image.fromarray(img)
+    t0 = time.time()
+    for _ in range(3):
+        pil.resize((512, 384), Image.LANCZOS)
+    cpu_ms = (time.time() - t0) / 3 * 1e3
+    nbytes = h * w * 3 + 2 * h * 512 * 3 + 3 * 384 * 512 * 4   # source read + 8-bit intermediate write/read + fp32 out
+    return {"image": "4032x3024 RGB8 -> 3x384x512 fp32 (LANCZOS, crop, normalise)", "gpu_us_per_image": us,
+            "gpu_images_per_sec": 1e6 / us, "algorithmic_bytes": nbytes, "achieved_gbs": nbytes / us / 1e3,
+            "frac_of_measured_hbm": nbytes / us / 1e3 / hbm_gbs, "pillow_cpu_ms_per_image_1_core": cpu_ms,
+            "note": "decode (PIL, host threads) and the H2D copy of the decoded image are outside this number"}
+
+
 def attention_roofline(timer, n_views, ms_step, clocks, peak_tf, peak_src):
     att = [(b, h, sq, skv, a.elapsed_time(z)) for (b, h, sq, skv, a, z) in timer if skv == n_views * P_TOK]
     if not att:
@@ -521,6 +554,10 @@ def run_ours(args, rank, world, local_rank):
             extra["N1000_8gpu"] = extra_config(1000)
         if world == 1:
             extra["decoder_gemms_M23552"] = gemm_rates(dev, peak_tf)
+            try:
+                extra["ingest_12mpix"] = ingest_rates(dev, hbm)
+            except Exception as e:  # context only
+                extra["ingest_12mpix"] = {"unavailable": repr(e)[:200]}
     if rank == 0 and world == 1 and not args.no_extras and not args.no_library_bar:
         extra["library_bar_N32"] = library_bar(32, dev)
     if rank != 0:

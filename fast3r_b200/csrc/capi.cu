@@ -383,6 +383,34 @@ int f3r_attention_x3(const float* q, int32_t ldq, const float* kv, int32_t ldkv,
   return check(f3r::launch_attention_x3(tq3, tk3, tv2, a, st), "f3r_attention_x3");
 }
 
+int f3r_resample_ksize(int32_t in_size, int32_t out_size, int32_t filter) {
+  if (in_size <= 0 || out_size <= 0 || (filter != 0 && filter != 1)) return -1;
+  return f3r::resample_ksize(in_size, out_size, filter);
+}
+
+int f3r_resample_coeffs(int32_t in_size, int32_t out_size, int32_t filter, int32_t* bounds, int32_t* kk) {
+  if (in_size <= 0 || out_size <= 0 || (filter != 0 && filter != 1) || !bounds || !kk) {
+    fail("f3r_resample_coeffs: bad arguments");
+    return -1;
+  }
+  return f3r::resample_coeffs(in_size, out_size, filter, bounds, kk);
+}
+
+int f3r_ingest_rgb8(const uint8_t* src, int32_t h, int32_t w, int32_t oh, int32_t ow, const int32_t* hb, const int32_t* hk,
+                    int32_t hks, int32_t h_span_max, const int32_t* vb, const int32_t* vk, int32_t vks, uint8_t* tmp,
+                    int32_t left, int32_t top, int32_t cw, int32_t ch, float* out, void* stream) {
+  if (!src || !out) return fail("f3r_ingest_rgb8: null operand");
+  if (h <= 0 || w <= 0 || oh <= 0 || ow <= 0 || cw <= 0 || ch <= 0) return fail("f3r_ingest_rgb8: bad shape");
+  if (left < 0 || top < 0 || left + cw > ow || top + ch > oh) return fail("f3r_ingest_rgb8: crop box outside the resized image");
+  if ((ow != w) != (hk != nullptr) || (oh != h) != (vk != nullptr))
+    return fail("f3r_ingest_rgb8: tap tables must be given exactly for the resized dimensions");
+  if (hk && (!hb || !tmp || hks <= 0 || h_span_max <= 0)) return fail("f3r_ingest_rgb8: incomplete horizontal pass arguments");
+  if (vk && (!vb || vks <= 0)) return fail("f3r_ingest_rgb8: incomplete vertical pass arguments");
+  g_launches += hk ? 2 : 1;
+  return check(f3r::launch_ingest(src, h, w, oh, ow, hb, hk, hks, h_span_max, vb, vk, vks, tmp, left, top, cw, ch, out,
+                                  static_cast<cudaStream_t>(stream)), "f3r_ingest_rgb8");
+}
+
 int f3r_cast_bf16(const float* in, void* out, size_t count, void* stream) {
   if (!in || !out) return fail("f3r_cast_bf16: null operand");
   g_launches++;

@@ -82,4 +82,11 @@ cudaError_t launch_upsample2x(const void* in, void* out, int f32, int n, int H, 
                               int Hfull, int Wfull, cudaStream_t stream);
 cudaError_t launch_cast_bf16(const float* in, void* out, size_t n, cudaStream_t stream);
 
+// image ingest (ingest.cu)
+int resample_ksize(int in_size, int out_size, int filter);
+int resample_coeffs(int in_size, int out_size, int filter, int32_t* bounds, int32_t* kk);
+cudaError_t launch_ingest(const uint8_t* src, int h, int w, int oh, int ow, const int32_t* hb, const int32_t* hk, int hks,
+                          int h_span_max, const int32_t* vb, const int32_t* vk, int vks, uint8_t* tmp, int left, int top,
+                          int cw, int ch, float* out, cudaStream_t stream);
+
 }  // namespace f3r

@@ -40,7 +40,7 @@ ABI_VERSION = 2
 EXPORTS = ["f3r_last_error", "f3r_abi_version", "f3r_gemm_desc_size", "f3r_launch_count", "f3r_gemm", "f3r_attention",
            "f3r_layernorm", "f3r_im2col_patch", "f3r_im2col3x3s2", "f3r_upsample2x", "f3r_cast_bf16", "f3r_split3",
            "f3r_add_f32", "f3r_attention_x3_workspace", "f3r_attention_x3", "f3r_set_option", "f3r_attention_partial",
-           "f3r_attention_merge"]
+           "f3r_attention_merge", "f3r_resample_ksize", "f3r_resample_coeffs", "f3r_ingest_rgb8"]
 
 _lib = None
 
@@ -66,6 +66,14 @@ def load() -> C.CDLL:
                                         C.c_int32, C.c_void_p]
     lib.f3r_attention_partial.restype = C.c_int
     lib.f3r_attention_merge.restype = C.c_int
+    lib.f3r_resample_ksize.argtypes = [C.c_int32, C.c_int32, C.c_int32]
+    lib.f3r_resample_ksize.restype = C.c_int
+    lib.f3r_resample_coeffs.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.f3r_resample_coeffs.restype = C.c_int
+    lib.f3r_ingest_rgb8.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                    C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
+                                    C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.f3r_ingest_rgb8.restype = C.c_int
     lib.f3r_set_option.argtypes = [C.c_char_p, C.c_int32]
     lib.f3r_set_option.restype = C.c_int
     lib.f3r_attention.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
