@@ -23,46 +23,67 @@ __device__ __forceinline__ uint8_t ing_clip8(int v) {
   return static_cast<uint8_t>(min(max(v, 0), 255));
 }
 
-// ---- horizontal pass: src [h][w][3] u8 -> dst [h][ow][3] u8.  Block = 64 output columns x 8 rows; the taps of the 64
-// columns ([k][col], conflict-free) and the source spans of the 8 rows are staged in shared memory.
+// ---- horizontal pass: src [h][w][3] u8 -> dst [h][ow][3] u8.  Block = 64 output columns x ING_ROWS_PER_BLOCK rows, walked
+// 8 rows at a time; the taps of the 64 columns ([k][col], conflict-free) are staged in shared memory once per block, the
+// source spans of 8 rows per step (4-byte aligned, coalesced word loads).
+constexpr int ING_ROWS_PER_BLOCK = 32;
 __global__ void __launch_bounds__(ING_COLS* ING_ROWS)
 resize_h_kernel(const uint8_t* __restrict__ src, int h, int w, uint8_t* __restrict__ dst, int ow,
                 const int32_t* __restrict__ bounds, const int32_t* __restrict__ kk, int ksize, int span_max) {
   extern __shared__ int32_t ing_smem[];
-  int32_t* sk = ing_smem;                                              // [ksize][ING_COLS]
-  uint8_t* sp = reinterpret_cast<uint8_t*>(ing_smem + ksize * ING_COLS);  // [ING_ROWS][span_bytes (4-aligned)]
-  const int c0 = blockIdx.x * ING_COLS, y0 = blockIdx.y * ING_ROWS;
+  int32_t* sk = ing_smem;                                                 // [ksize][ING_COLS]
+  uint8_t* sp = reinterpret_cast<uint8_t*>(ing_smem + ksize * ING_COLS);  // [ING_ROWS][span_pad]
+  const int c0 = blockIdx.x * ING_COLS, yb = blockIdx.y * ING_ROWS_PER_BLOCK;
   const int tx = threadIdx.x % ING_COLS, ty = threadIdx.x / ING_COLS;
   const int ncols = min(ING_COLS, ow - c0);
-  const int x_lo = __ldg(bounds + 2 * c0);                            // first source pixel of the block
+  const int x_lo = __ldg(bounds + 2 * c0);                               // first source pixel of the block
   const int last = c0 + ncols - 1;
   const int x_hi = __ldg(bounds + 2 * last) + __ldg(bounds + 2 * last + 1);  // one past the last source pixel
-  const int span = (x_hi - x_lo) * 3;                                 // bytes per row
-  const int span_pad = (span_max * 3 + 3) & ~3;
+  const int span_pad = ((span_max * 3 + 3) & ~3) + 4;                    // (+4: room for the alignment shift)
   for (int i = threadIdx.x; i < ksize * ING_COLS; i += blockDim.x) {
     const int k = i / ING_COLS, c = i % ING_COLS;
     sk[i] = c < ncols ? __ldg(kk + static_cast<size_t>(c0 + c) * ksize + k) : 0;
   }
-  for (int r = 0; r < ING_ROWS; ++r) {
-    const int y = y0 + r;
-    if (y >= h) break;
-    const uint8_t* row = src + (static_cast<size_t>(y) * w + x_lo) * 3;
-    for (int i = threadIdx.x; i < span; i += blockDim.x) sp[r * span_pad + i] = __ldg(row + i);
+  const bool active = tx < ncols;
+  const int xmin = active ? __ldg(bounds + 2 * (c0 + tx)) - x_lo : 0, n = active ? __ldg(bounds + 2 * (c0 + tx) + 1) : 0;
+  for (int y0 = yb; y0 < min(yb + ING_ROWS_PER_BLOCK, h); y0 += ING_ROWS) {
+    __syncthreads();  // taps staged / previous step's spans consumed
+    for (int r = 0; r < ING_ROWS; ++r) {
+      const int y = y0 + r;
+      if (y >= h) break;
+      // bytes [b0, b1) of the image, fetched as aligned 32-bit words [a0, a1)
+      const size_t b0 = (static_cast<size_t>(y) * w + x_lo) * 3, b1 = (static_cast<size_t>(y) * w + x_hi) * 3;
+      const size_t a0 = b0 & ~static_cast<size_t>(3);
+      const size_t total = static_cast<size_t>(h) * w * 3;
+      const int nwords = static_cast<int>((b1 - a0 + 3) >> 2);
+      uint32_t* dstw = reinterpret_cast<uint32_t*>(sp + r * span_pad);
+      for (int i = threadIdx.x; i < nwords; i += blockDim.x) {
+        const size_t off = a0 + static_cast<size_t>(i) * 4;
+        uint32_t v;
+        if (off + 4 <= total) v = __ldg(reinterpret_cast<const uint32_t*>(src + off));
+        else {  // last word of the image: assemble from bytes
+          v = 0;
+          for (int bidx = 0; bidx < 4 && off + bidx < total; ++bidx) v |= static_cast<uint32_t>(src[off + bidx]) << (8 * bidx);
+        }
+        dstw[i] = v;
+      }
+    }
+    __syncthreads();
+    const int y = y0 + ty;
+    if (active && y < h) {
+      const size_t b0 = (static_cast<size_t>(y) * w + x_lo) * 3;
+      const uint8_t* px = sp + ty * span_pad + (b0 & 3) + xmin * 3;
+      int a0 = 1 << (ING_PREC - 1), a1 = a0, a2 = a0;
+      for (int t = 0; t < n; ++t) {
+        const int kv = sk[t * ING_COLS + tx];
+        a0 += static_cast<int>(px[3 * t + 0]) * kv;
+        a1 += static_cast<int>(px[3 * t + 1]) * kv;
+        a2 += static_cast<int>(px[3 * t + 2]) * kv;
+      }
+      uint8_t* o = dst + (static_cast<size_t>(y) * ow + c0 + tx) * 3;
+      o[0] = ing_clip8(a0); o[1] = ing_clip8(a1); o[2] = ing_clip8(a2);
+    }
   }
-  __syncthreads();
-  const int y = y0 + ty;
-  if (tx >= ncols || y >= h) return;
-  const int xmin = __ldg(bounds + 2 * (c0 + tx)) - x_lo, n = __ldg(bounds + 2 * (c0 + tx) + 1);
-  const uint8_t* px = sp + ty * span_pad + xmin * 3;
-  int a0 = 1 << (ING_PREC - 1), a1 = a0, a2 = a0;
-  for (int t = 0; t < n; ++t) {
-    const int kv = sk[t * ING_COLS + tx];
-    a0 += static_cast<int>(px[3 * t + 0]) * kv;
-    a1 += static_cast<int>(px[3 * t + 1]) * kv;
-    a2 += static_cast<int>(px[3 * t + 2]) * kv;
-  }
-  uint8_t* o = dst + (static_cast<size_t>(y) * ow + c0 + tx) * 3;
-  o[0] = ing_clip8(a0); o[1] = ing_clip8(a1); o[2] = ing_clip8(a2);
 }
 
 // ---- vertical pass fused with the center crop and ToTensor + Normalize:
@@ -104,11 +125,11 @@ cudaError_t launch_ingest(const uint8_t* src, int h, int w, int oh, int ow, cons
                           int cw, int ch, float* out, cudaStream_t stream) {
   const uint8_t* mid = src;
   if (hk != nullptr) {
-    const size_t smem = static_cast<size_t>(hks) * ING_COLS * 4 + static_cast<size_t>(ING_ROWS) * ((h_span_max * 3 + 3) & ~3);
+    const size_t smem = static_cast<size_t>(hks) * ING_COLS * 4 + static_cast<size_t>(ING_ROWS) * (((h_span_max * 3 + 3) & ~3) + 4);
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(resize_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
-    dim3 grid((ow + ING_COLS - 1) / ING_COLS, (h + ING_ROWS - 1) / ING_ROWS);
+    dim3 grid((ow + ING_COLS - 1) / ING_COLS, (h + ING_ROWS_PER_BLOCK - 1) / ING_ROWS_PER_BLOCK);
     resize_h_kernel<<<grid, ING_COLS * ING_ROWS, smem, stream>>>(src, h, w, tmp, ow, hb, hk, hks, h_span_max);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;

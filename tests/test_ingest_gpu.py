@@ -7,7 +7,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 SIZES = [(640, 480), (4032, 3024), (3024, 4032), (300, 200), (1000, 1000), (97, 131), (512, 384), (513, 384), (2000, 350),
-         (1920, 1080), (5000, 17), (64, 64)]
+         (1920, 1080), (5000, 170), (64, 64), (4000, 3000), (200, 4097)]
 
 
 def _img(w, h, seed):
