@@ -504,6 +504,9 @@ def run_ours(args, rank, world, local_rank):
     extra = {}
     if sp_trace is not None:
         extra["sp_attention_trace_rank0"] = sp_trace
+        kvx = next(iter(sp._kvx.values()), None)
+        extra["sp_kv_transport"] = ("copy-engine pulls from symmetric peer memory (torch symmetric memory)"
+                                    if (kvx is not None and kvx.sym_state) else "NCCL all-gather on a side stream")
     # ================= sharded vs un-sharded parity of THIS run (world > 1) =================
     if world > 1:
         torch.manual_seed(7)

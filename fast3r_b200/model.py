@@ -520,14 +520,14 @@ class Fast3R(nn.Module, _HubMixin, repo_url="https://github.com/facebookresearch
             scale = hd ** -0.5
         hidden = dec.dec_blocks[0].mlp.fc1.weight.shape[0]
         ws = self._workspace(M, D, hidden, dev, x3)
-        if kv_exchange is not None:
-            slot = kv_exchange.kv_workspace(ws["kv"].dtype, dev)
-            if slot is not None:
-                ws["kv"] = slot  # the QKV GEMM writes K|V straight into this rank's slot of the gather buffer
         depth = dec.depth
         hooks = {depth * 2 // 4: None, depth * 3 // 4: None}
         self._tap("dec_embed", x)
         for i, w in enumerate(P_["dec"]):
+            if kv_exchange is not None:
+                slot = kv_exchange.kv_workspace(ws["kv"].dtype, dev)
+                if slot is not None:
+                    ws["kv"] = slot  # the QKV GEMM writes K|V straight into this rank's exchange slot of this layer
             self._block(x, w, ws, batch=B, seq=n_local * P, heads=dec.num_heads, eps=1e-5, scale=scale,
                         kv_exchange=kv_exchange, x3=x3)
             self._tap(f"dec_block{i}", x)

@@ -9,6 +9,7 @@ broadcast to all ranks so the result equals the single-device forward whatever t
 """
 from __future__ import annotations
 
+import os
 from typing import List, Tuple
 
 import torch
@@ -56,6 +57,36 @@ class KVExchange:
         self.pad = None
         self.comm_stream = None
         self.parts = None
+        self.layer = 0
+        self.sym = None          # symmetric-memory transport: (2, s_local, C) K|V slots of this rank, double-buffered per layer
+        self.sym_state = None    # None: not tried yet, True / False
+
+    def _setup_symmetric(self, like: torch.Tensor) -> bool:
+        """Copy-engine transport: every rank exposes its K|V slot through torch symmetric memory (CUDA IPC over NVLink);
+        peers PULL it with DMA copies that need no SMs.  All ranks must agree, else everybody falls back to NCCL."""
+        sp = self.sp
+        ok = 1
+        try:
+            if sp.transport == "nccl" or os.environ.get("F3R_SP_TRANSPORT", "") == "nccl":
+                raise RuntimeError("symmetric-memory transport disabled")
+            import torch.distributed._symmetric_memory as symm
+            group = sp.group if sp.group is not None else dist.group.WORLD
+            C = 2 * self.dim
+            sym = symm.empty((2, self.s_local, C), dtype=like.dtype, device=like.device)
+            hdl = symm.rendezvous(sym, group)
+            peers = [hdl.get_buffer(r, (2, self.s_local, C), like.dtype) for r in range(sp.world)]
+            streams = [torch.cuda.Stream(device=like.device) for _ in range(max(1, min(4, sp.world - 1)))]
+        except Exception as e:  # noqa: BLE001
+            ok = 0
+            why = repr(e)[:200]
+        flag = torch.tensor([ok], device=like.device, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=sp.group)
+        if int(flag.item()) == 1:
+            self.sym, self.hdl, self.peers, self.copy_streams = sym, hdl, peers, streams
+            return True
+        if sp.rank == 0 and ok == 0 and sp.transport != "nccl" and os.environ.get("F3R_SP_TRANSPORT", "") != "nccl":
+            print(f"[fast3r_b200] symmetric-memory K|V transport unavailable ({why}); using the NCCL all-gather", flush=True)
+        return False
 
     def _ensure(self, like: torch.Tensor):
         if self.buf is None or self.buf.dtype != like.dtype or self.buf.device != like.device:
@@ -69,10 +100,16 @@ class KVExchange:
         return self.even and self.batch == 1 and dtype == torch.bfloat16 and device.type == "cuda" and self.sp.overlap
 
     def kv_workspace(self, dtype, device):
-        """Where the QKV GEMM should write this rank's K|V (None: any buffer; attend() copies)."""
+        """Where the QKV GEMM of the NEXT decoder layer should write this rank's K|V (None: any buffer; attend() copies).
+        Called once per layer by Fast3R._decode."""
         if not self.fast(dtype, device):
             return None
-        self._ensure(torch.empty(0, dtype=dtype, device=device))
+        like = torch.empty(0, dtype=dtype, device=device)
+        self._ensure(like)
+        if self.sym_state is None:
+            self.sym_state = self._setup_symmetric(like)
+        if self.sym_state:
+            return self.sym[self.layer & 1]
         return self.buf[self.sp.rank]
 
     def attend(self, ops, q, kv, att, *, heads: int, scale: float, x3: bool):
@@ -90,7 +127,10 @@ class KVExchange:
                                                         skv=self.s_total, scale=scale)
             return
         # ---- overlapped path
-        slot = self.buf[sp.rank]
+        use_sym = bool(self.sym_state)
+        par = self.layer & 1
+        self.layer += 1
+        slot = self.sym[par] if use_sym else self.buf[sp.rank]
         if kv.data_ptr() != slot.data_ptr():
             slot.copy_(kv)
         compute = torch.cuda.current_stream(kv.device)
@@ -99,17 +139,39 @@ class KVExchange:
         if ev:
             ev[0].record(compute)
         self.comm_stream.wait_stream(compute)  # K|V of this layer is complete; previous layer's readers are done
-        with torch.cuda.stream(self.comm_stream):
-            if ev:
-                ev[4].record(self.comm_stream)
-            dist.all_gather_into_tensor(self.buf.view(-1, C), slot, group=sp.group)
+        if use_sym:
+            # every rank's K|V of this layer sits in its symmetric slot `par`: barrier on the side stream, then pull the
+            # peers' slots with copy-engine DMA (no SMs, unlike NCCL's kernels) on a few streams in parallel.  The slot is
+            # reused two layers later; by then every peer has passed the next layer's barrier, i.e. finished these pulls.
+            with torch.cuda.stream(self.comm_stream):
+                if ev:
+                    ev[4].record(self.comm_stream)
+                self.hdl.barrier(channel=par)
+            ready = torch.cuda.Event()
+            ready.record(self.comm_stream)
+            for i in range(1, sp.world):
+                p_ = (sp.rank + i) % sp.world   # staggered so that not all ranks hit the same peer first
+                st = self.copy_streams[(i - 1) % len(self.copy_streams)]
+                st.wait_event(ready)
+                with torch.cuda.stream(st):
+                    self.buf[p_].copy_(self.peers[p_][par], non_blocking=True)
+            for st in self.copy_streams:
+                self.comm_stream.wait_stream(st)
             if ev:
                 ev[5].record(self.comm_stream)
+        else:
+            with torch.cuda.stream(self.comm_stream):
+                if ev:
+                    ev[4].record(self.comm_stream)
+                dist.all_gather_into_tensor(self.buf.view(-1, C), slot, group=sp.group)
+                if ev:
+                    ev[5].record(self.comm_stream)
         sp.bytes_exchanged += self.buf.numel() * self.buf.element_size()
         S, sl = self.s_total, self.s_local
         lo, hi = sp.rank * sl, (sp.rank + 1) * sl
         units = heads * ((sl + 255) // 256)
-        ranges = [(lo, sl)] + [r for r in ((0, lo), (hi, S - hi)) if r[1] > 0]   # local keys first, then the others
+        # local keys first (straight from this rank's slot), then the other ranks' ranges of the gather buffer
+        ranges = [(lo, sl)] + [r for r in ((0, lo), (hi, S - hi)) if r[1] > 0]
         splits = [ops.pick_kv_split(units, (n + 127) // 128) for _, n in ranges]
         slots = sum(splits)
         if self.parts is None or self.parts[0].shape[0] < slots:
@@ -123,8 +185,12 @@ class KVExchange:
                 if ev:
                     ev[1].record(compute)
                 compute.wait_stream(self.comm_stream)  # the other ranks' keys have landed
-            ops.attention_partial(q, kv_all, part_o, part_lse, part_base=base, n_split=ns, batch=1, heads=heads, sq=sl,
-                                  kv_rows_total=S, kv_row0=row0, skv=n, scale=scale)
+            if i == 0 and use_sym:   # the local keys are read where the QKV GEMM wrote them
+                ops.attention_partial(q, slot, part_o, part_lse, part_base=base, n_split=ns, batch=1, heads=heads, sq=sl,
+                                      kv_rows_total=sl, kv_row0=0, skv=n, scale=scale)
+            else:
+                ops.attention_partial(q, kv_all, part_o, part_lse, part_base=base, n_split=ns, batch=1, heads=heads,
+                                      sq=sl, kv_rows_total=S, kv_row0=row0, skv=n, scale=scale)
             base += ns
         if len(ranges) == 1:
             compute.wait_stream(self.comm_stream)
@@ -146,6 +212,8 @@ class SequenceParallel:
         self.gather_preds = gather_preds
         self.overlap = True   # False: always all-gather first, then one attention call (A/B measurements)
         self.timers = None    # set to a list to collect CUDA-event traces of KVExchange.attend (bench.py)
+        self.transport = "auto"   # "auto": copy-engine pulls from symmetric peer memory if available, else NCCL; "nccl"
+        self._kvx = {}
         self._ranges = None
         self.bytes_exchanged = 0
 
@@ -170,7 +238,11 @@ class SequenceParallel:
         """Per-forward exchange object for the fusion decoder (one per `_decode` call)."""
         tok_per_view = s_local // (self._ranges[self.rank][1] - self._ranges[self.rank][0])
         rows = [(hi - lo) * tok_per_view for lo, hi in self._ranges]
-        return KVExchange(self, batch, s_local, dim, rows)
+        key = (batch, s_local, dim, tuple(rows))
+        if key not in self._kvx:   # buffers (and the symmetric-memory rendezvous) are reused across forwards
+            self._kvx = {key: KVExchange(self, batch, s_local, dim, rows)}
+        self._kvx[key].layer = 0
+        return self._kvx[key]
 
     def gather_results(self, final_results, num_views, batch, H, W, device):
         """All ranks end up with the preds of every view (API parity with the single-device forward)."""
