@@ -67,8 +67,13 @@ class KVExchange:
         sp = self.sp
         ok = 1
         try:
-            if sp.transport == "nccl" or os.environ.get("F3R_SP_TRANSPORT", "") == "nccl":
+            env = os.environ.get("F3R_SP_TRANSPORT", "")
+            if sp.transport == "nccl" or env == "nccl":
                 raise RuntimeError("symmetric-memory transport disabled")
+            # measured (profiles/r02_notes.md): with 2 ranks the DMA pulls hide completely behind the local-chunk attention
+            # while NCCL's kernels starve for SMs (62.9 -> 60.9 ms at N=32); with 8 ranks both take ~0.26 ms per layer
+            if sp.transport == "auto" and env != "symm" and sp.world > 4:
+                raise RuntimeError("NCCL all-gather preferred for more than 4 ranks")
             import torch.distributed._symmetric_memory as symm
             group = sp.group if sp.group is not None else dist.group.WORLD
             C = 2 * self.dim
@@ -84,7 +89,7 @@ class KVExchange:
         if int(flag.item()) == 1:
             self.sym, self.hdl, self.peers, self.copy_streams = sym, hdl, peers, streams
             return True
-        if sp.rank == 0 and ok == 0 and sp.transport != "nccl" and os.environ.get("F3R_SP_TRANSPORT", "") != "nccl":
+        if sp.rank == 0 and ok == 0 and "preferred" not in why and "disabled" not in why:
             print(f"[fast3r_b200] symmetric-memory K|V transport unavailable ({why}); using the NCCL all-gather", flush=True)
         return False
 
@@ -212,7 +217,8 @@ class SequenceParallel:
         self.gather_preds = gather_preds
         self.overlap = True   # False: always all-gather first, then one attention call (A/B measurements)
         self.timers = None    # set to a list to collect CUDA-event traces of KVExchange.attend (bench.py)
-        self.transport = "auto"   # "auto": copy-engine pulls from symmetric peer memory if available, else NCCL; "nccl"
+        self.transport = "auto"   # "auto": copy-engine pulls from symmetric peer memory for <= 4 ranks (if available),
+        #                           NCCL all-gather otherwise; "symm" / "nccl" force one (also F3R_SP_TRANSPORT)
         self._kvx = {}
         self._ranges = None
         self.bytes_exchanged = 0
