@@ -144,20 +144,28 @@ cudaError_t launch_im2col3x3s2(const void* in, void* out, int n, int H, int W, i
 // F.interpolate(scale_factor=2, mode="bilinear", align_corners=True) (fast3r/croco/models/dpt_block.py:234-247,
 // 374): src = dst * (in-1)/(full-1), full = 2*in; only the top-left Ho x Wo window of the full output is produced
 // (Ho < full implements the crop of refinenet4's output, fast3r/dust3r/heads/dpt_head.py:69-71).
+constexpr int UPS_ROWS = 8;
 __global__ void __launch_bounds__(256) upsample2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out,
                                                          int H, int W, int C8, int c8_shift, int Ho, int Wo, float sy,
                                                          float sx) {
-  // blockIdx.z = image, blockIdx.y = output row, x covers (ox, 8-channel group) of that row: the row interpolation
-  // weights are per block, the only per-thread index math is one shift/mask (C8 is a power of two: 16 or 32 here)
-  const int oy = blockIdx.y;
+  // blockIdx.z = image, blockIdx.y = group of UPS_ROWS output rows, x covers (ox, 8-channel group) of a row.  A block
+  // walks UPS_ROWS consecutive output rows of the same columns: they interpolate between the same 2-3 input rows, so every
+  // input pixel is fetched from L2 once per block and served from L1 afterwards (one-row blocks read each input 4x from
+  // L2, which capped the kernel at a third of the HBM rate - profiles/r02_ncu_kernel_families.txt).
   const size_t im = blockIdx.z;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= Wo * C8) return;
   const int c = t & (C8 - 1), ox = t >> c8_shift;
-  const float fy = sy * oy, fx = sx * ox;
-  const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
-  const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
-  const float ly = fy - y0, lx = fx - x0;
+  const float fx = sx * ox;
+  const int x0 = static_cast<int>(fx);
+  const int x1 = min(x0 + 1, W - 1);
+  const float lx = fx - x0;
+#pragma unroll 1
+  for (int oy = blockIdx.y * UPS_ROWS; oy < min((static_cast<int>(blockIdx.y) + 1) * UPS_ROWS, Ho); ++oy) {
+  const float fy = sy * oy;
+  const int y0 = static_cast<int>(fy);
+  const int y1 = min(y0 + 1, H - 1);
+  const float ly = fy - y0;
   const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
   const uint4* base = in + im * H * W * C8 + c;
   const uint4 a = __ldg(base + (static_cast<size_t>(y0) * W + x0) * C8);
@@ -174,6 +182,7 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const uint4* __restrict
     ow[i] = pack_bf16(lo, hi);
   }
   out[((im * Ho + oy) * Wo + ox) * C8 + c] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+  }
 }
 // fp32 NHWC variant (parity mode): one float4 (4 channels) per thread
 __global__ void __launch_bounds__(256) upsample2x_f32_kernel(const float4* __restrict__ in, float4* __restrict__ out,
@@ -226,7 +235,7 @@ cudaError_t launch_upsample2x(const void* in, void* out, int f32, int n, int H, 
   if (n > 65535 || Ho > 65535) return cudaErrorInvalidValue;
   const float sy = static_cast<float>(H - 1) / static_cast<float>(Hfull - 1);
   const float sx = static_cast<float>(W - 1) / static_cast<float>(Wfull - 1);
-  dim3 grid((Wo * C8 + 255) / 256, Ho, n);
+  dim3 grid((Wo * C8 + 255) / 256, (Ho + UPS_ROWS - 1) / UPS_ROWS, n);
   upsample2x_kernel<<<grid, 256, 0, stream>>>(static_cast<const uint4*>(in), static_cast<uint4*>(out), H, W, C8, shift,
                                               Ho, Wo, sy, sx);
   return cudaGetLastError();

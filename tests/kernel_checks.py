@@ -218,6 +218,24 @@ def check_attention_autosplit(batch=1, heads=4, sq=600, skv=4000, scale=0.16019,
     return rel(b, a), 3e-3, dict(auto_split=ns)
 
 
+def check_attention_n320_slices(heads=1, sq=256, skv=235520, scale=0.16019, seed=99):
+    """The N=320 key count (235 520 keys = 1 840 key blocks): one pass over all keys vs 4 key slices merged by their
+    log-sum-exp - two different accumulation orders of the same softmax must agree (size-independent property)."""
+    D = heads * 64
+    q = _rand((sq, D), seed)
+    kv = _rand((skv, 2 * D), seed + 1)
+    a = torch.zeros(sq, D, dtype=torch.bfloat16, device="cuda")
+    b = torch.zeros_like(a)
+    ops.attention(q, kv, a, batch=1, heads=heads, sq=sq, skv=skv, scale=scale, kv_split=1)
+    ops.attention(q, kv, b, batch=1, heads=heads, sq=sq, skv=skv, scale=scale, kv_split=4)
+    # sanity against fp32 math on a subset of the rows
+    qs = q[:32].float().reshape(32, heads, 64).transpose(0, 1)
+    kh = kv[:, :D].float().reshape(skv, heads, 64).transpose(0, 1)
+    vh = kv[:, D:].float().reshape(skv, heads, 64).transpose(0, 1)
+    ref = (((qs @ kh.transpose(-2, -1)) * scale).softmax(-1) @ vh).transpose(0, 1).reshape(32, D)
+    return max(rel(b, a), rel(a[:32], ref)), 8e-3, dict(slices_vs_single=rel(b, a), vs_fp32=rel(a[:32], ref))
+
+
 def check_layernorm(rows=1000, dim=1024, eps=1e-5, seed=100):
     x = _rand((rows, dim), seed, 2.0, torch.float32) + 0.5
     w, b = _rand((dim,), seed + 1, 1.0, torch.float32), _rand((dim,), seed + 2, 1.0, torch.float32)
@@ -391,6 +409,7 @@ ALL = [
     ("attn_ranges_merge", check_attention_ranges, {}),
     ("attn_ranges_merge_rank0", check_attention_ranges, dict(rank=0, world=3, chunk=500, sq=300)),
     ("attn_autosplit", check_attention_autosplit, {}),
+    ("attn_skv235520_slices", check_attention_n320_slices, {}),
     # the bench regime: 23 552 keys (N=32 views) = 184 key blocks of lazy-rescale accumulation, flat and peaky scores
     ("attn_skv23552", check_attention, dict(batch=1, heads=2, sq=512, skv=23552, scale=0.16019)),
     ("attn_skv23552_peaky", check_attention, dict(batch=1, heads=1, sq=256, skv=23552, scale=0.5, qscale=3.0)),
