@@ -37,10 +37,16 @@ class GemmDesc(C.Structure):
 
 
 ABI_VERSION = 2
+class BlockWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("norm1_w", "norm1_b", "norm2_w", "norm2_b", "qkv_w", "qkv_b", "proj_w", "proj_b",
+                                          "fc1_w", "fc1_b", "fc2_w", "fc2_b")]
+
+
 EXPORTS = ["f3r_last_error", "f3r_abi_version", "f3r_gemm_desc_size", "f3r_launch_count", "f3r_gemm", "f3r_attention",
            "f3r_layernorm", "f3r_im2col_patch", "f3r_im2col3x3s2", "f3r_upsample2x", "f3r_cast_bf16", "f3r_split3",
            "f3r_add_f32", "f3r_attention_x3_workspace", "f3r_attention_x3", "f3r_set_option", "f3r_attention_partial",
-           "f3r_attention_merge", "f3r_resample_ksize", "f3r_resample_coeffs", "f3r_ingest_rgb8"]
+           "f3r_attention_merge", "f3r_resample_ksize", "f3r_resample_coeffs", "f3r_ingest_rgb8",
+           "f3r_transformer_workspace", "f3r_transformer_blocks"]
 
 _lib = None
 
@@ -74,6 +80,12 @@ def load() -> C.CDLL:
                                     C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
                                     C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
     lib.f3r_ingest_rgb8.restype = C.c_int
+    lib.f3r_transformer_workspace.argtypes = [C.c_int32, C.c_int32, C.c_int32]
+    lib.f3r_transformer_workspace.restype = C.c_size_t
+    lib.f3r_transformer_blocks.argtypes = [C.POINTER(BlockWeights), C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                           C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_int32, C.c_int32, C.c_void_p,
+                                           C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.f3r_transformer_blocks.restype = C.c_int
     lib.f3r_set_option.argtypes = [C.c_char_p, C.c_int32]
     lib.f3r_set_option.restype = C.c_int
     lib.f3r_attention.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
