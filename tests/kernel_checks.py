@@ -406,6 +406,7 @@ ALL = [
     ("attn_24", check_attention, dict(batch=3, heads=2, sq=24, skv=24)),
     ("attn_long_3072", check_attention, dict(batch=1, heads=2, sq=512, skv=3072, scale=0.16019)),
     ("attn_peaky", check_attention, dict(batch=1, heads=2, sq=512, skv=2048, scale=0.5, qscale=3.0)),
+    ("attn_q9tiles_oddpair", check_attention, dict(batch=1, heads=2, sq=2300, skv=1000, scale=0.16019)),
     ("attn_ranges_merge", check_attention_ranges, {}),
     ("attn_ranges_merge_rank0", check_attention_ranges, dict(rank=0, world=3, chunk=500, sq=300)),
     ("attn_autosplit", check_attention_autosplit, {}),
