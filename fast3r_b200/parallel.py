@@ -16,6 +16,18 @@ import torch
 import torch.distributed as dist
 
 
+def _all_gather_into(out: torch.Tensor, inp: torch.Tensor, group=None) -> None:
+    """dist.all_gather_into_tensor that also works for CUDA tensors over a gloo group (staged through the host): lets two
+    ranks share ONE GPU in tests (NCCL refuses duplicate devices); NCCL groups take the direct call."""
+    if inp.is_cuda and dist.get_backend(group) == "gloo":
+        host_in = inp.detach().cpu().contiguous()
+        host_out = torch.empty(out.shape, dtype=out.dtype)
+        dist.all_gather_into_tensor(host_out, host_in, group=group)
+        out.copy_(host_out)
+        return
+    dist.all_gather_into_tensor(out, inp, group=group)
+
+
 def shard_views(num_views: int, world: int) -> List[Tuple[int, int]]:
     """Contiguous, balanced view ranges: the first (num_views % world) ranks get one extra view."""
     base, rem = divmod(num_views, world)
@@ -68,6 +80,8 @@ class KVExchange:
         ok = 1
         try:
             env = os.environ.get("F3R_SP_TRANSPORT", "")
+            if dist.get_backend(sp.group) != "nccl":
+                raise RuntimeError("symmetric-memory transport disabled (not an NCCL group)")
             if sp.transport == "nccl" or env == "nccl":
                 raise RuntimeError("symmetric-memory transport disabled")
             # measured (profiles/r02_notes.md): with 2 ranks the DMA pulls hide completely behind the local-chunk attention
@@ -84,7 +98,8 @@ class KVExchange:
         except Exception as e:  # noqa: BLE001
             ok = 0
             why = repr(e)[:200]
-        flag = torch.tensor([ok], device=like.device, dtype=torch.int32)
+        on_gpu = dist.get_backend(sp.group) == "nccl"
+        flag = torch.tensor([ok], device=like.device if on_gpu else "cpu", dtype=torch.int32)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=sp.group)
         if int(flag.item()) == 1:
             self.sym, self.hdl, self.peers, self.copy_streams = sym, hdl, peers, streams
@@ -125,7 +140,7 @@ class KVExchange:
             if not self.even:
                 self.pad.view(self.batch, self.mx, C)[:, :self.s_local] = kv.view(self.batch, self.s_local, C)
                 src = self.pad
-            dist.all_gather_into_tensor(self.buf.view(-1, C), src.contiguous(), group=sp.group)
+            _all_gather_into(self.buf.view(-1, C), src.contiguous(), group=sp.group)
             sp.bytes_exchanged += self.buf.numel() * self.buf.element_size()
             kv_all = assemble_kv(self.buf, self.batch, self.rows)
             (ops.attention_x3 if x3 else ops.attention)(q, kv_all, att, batch=self.batch, heads=heads, sq=self.s_local,
@@ -168,7 +183,7 @@ class KVExchange:
             with torch.cuda.stream(self.comm_stream):
                 if ev:
                     ev[4].record(self.comm_stream)
-                dist.all_gather_into_tensor(self.buf.view(-1, C), slot, group=sp.group)
+                _all_gather_into(self.buf.view(-1, C), slot, group=sp.group)
                 if ev:
                     ev[5].record(self.comm_stream)
         sp.bytes_exchanged += self.buf.numel() * self.buf.element_size()
@@ -263,7 +278,7 @@ class SequenceParallel:
             send = torch.zeros((mxv * batch,) + tuple(tail), dtype=loc.dtype, device=device)
             send[: loc.shape[0]] = loc
             recv = torch.empty((self.world, mxv * batch) + tuple(tail), dtype=loc.dtype, device=device)
-            dist.all_gather_into_tensor(recv.view((-1,) + tuple(tail)), send, group=self.group)
+            _all_gather_into(recv.view((-1,) + tuple(tail)), send, group=self.group)
             for r, (a, b) in enumerate(self._ranges):
                 for i in range(a, b):
                     out[i][k] = recv[r, (i - a) * batch:(i - a + 1) * batch]

@@ -12,8 +12,14 @@ from fast3r_b200.parallel import enable_sequence_parallel  # noqa: E402
 from tests.golden.synth import synth_state_dict, synth_images  # noqa: E402
 
 rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-torch.cuda.set_device(lr)
-dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+# SP_ONE_GPU=1: all ranks share cuda:0 and talk over gloo (host-staged collectives) - exercises the sharded forward,
+# the key-range partials and the LSE merge on a 1-GPU box; the default is one GPU per rank over NCCL
+one_gpu = os.environ.get("SP_ONE_GPU", "0") == "1"
+torch.cuda.set_device(0 if one_gpu else lr)
+if one_gpu:
+    dist.init_process_group("gloo")
+else:
+    dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
 ok = True
 for (n_views, batch, H, W) in [(5, 1, 64, 96), (4, 2, 48, 64), (2 * world, 1, 96, 128)]:
     model = Fast3R(*tiny_args()).eval()
@@ -34,7 +40,7 @@ for (n_views, batch, H, W) in [(5, 1, 64, 96), (4, 2, 48, 64), (2 * world, 1, 96
             d = (a[k].float() - b[k].float()).abs().max().item() / (b[k].float().abs().max().item() + 1e-30)
             worst = max(worst, d)
     print(f"  rank {rank}: worst {worst:.3e}", flush=True)
-    t = torch.tensor([worst], device="cuda")
+    t = torch.tensor([worst], device="cpu" if one_gpu else "cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     fast = batch == 1 and n_views % world == 0   # overlapped exchange: key-range partials merged in fp32
     if rank == 0:
