@@ -14,7 +14,8 @@ oracle is pinned against outputs of the reference ITSELF, run in the build conta
 ``tests/golden/make_golden.py`` (which imports /root/reference through
 ``oracle/ref_harness.py``); the resulting fixtures live in ``tests/golden/*.pt`` and
 ``tests/test_oracle_vs_golden.py`` checks this file against them (per-stage taps and final
-preds, tiny model end-to-end and ViT-L-width single ops).
+preds, tiny model end-to-end, ViT-L-width single ops, and the full ViT-L/512 at N=4 views
+512x368 = BASELINE configs[0], through the reference's own inference(dtype="32")).
 """
 from __future__ import annotations
 
