@@ -54,6 +54,8 @@ def _tables(in_size: int, out_size: int, filt: int, device):
                                        kk.ctypes.data_as(C.c_void_p))
         if span < 0:
             raise RuntimeError("f3r_resample_coeffs failed: " + lib.f3r_last_error().decode())
+        if len(_TABLES) >= 256:   # photo collections have a handful of geometries; bound the cache anyway
+            _TABLES.pop(next(iter(_TABLES)))
         _TABLES[key] = (torch.from_numpy(bounds).to(device), torch.from_numpy(kk).to(device), ks, span)
     return _TABLES[key]
 
