@@ -159,3 +159,22 @@ def test_sequence_parallel_host_logic_gloo(n_views, batch):
     for p in procs:
         p.join(120)
     assert dict(ret) == {0: True, 1: True}
+
+
+def test_pick_kv_split_invariants():
+    """ops.pick_kv_split: key slicing only when it fills more of the 148 SMs, every slice keeps >= 16 key blocks, and the
+    measured shapes map to the measured choices (profiles/r02_notes.md)."""
+    from fast3r_b200.ops import pick_kv_split, NUM_SMS
+    for units in (1, 16, 64, 148, 192, 368, 443, 444, 736, 1472, 23552):
+        for blocks in (1, 6, 15, 16, 23, 32, 92, 184, 1840):
+            s = pick_kv_split(units, blocks)
+            assert 1 <= s <= 8
+            assert s == 1 or blocks // s >= 16
+            if units >= 3 * NUM_SMS:
+                assert s == 1
+            waves = lambda k: -(-units * k // NUM_SMS) / k  # noqa: E731
+            assert waves(s) <= waves(1) + 1e-9            # never worse than one slice
+    assert pick_kv_split(192, 184) == 3      # N=32 shard on 8 GPUs (2 waves at 65 % -> 4 waves of thirds)
+    assert pick_kv_split(368, 184) == 2      # 4 GPUs
+    assert pick_kv_split(1472, 184) == 1     # one GPU
+    assert pick_kv_split(192, 23) == 1       # N=4: slices would be too short
