@@ -146,6 +146,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();                // q / kv come from the preceding QKV GEMM: no global access above this line
+  pdl_launch_dependents();
 
   if (warp < 4) {
     // register budget (must balance inside the CTA's launch allocation):
@@ -400,9 +402,15 @@ static cudaError_t launch_attention_t(const CUtensorMap& tq, const CUtensorMap& 
   cudaError_t e = cudaFuncSetAttribute(attention_kernel<kEmu, kSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        ATT_SMEM_BYTES);
   if (e != cudaSuccess) return e;
-  const int grid = a.batch * a.heads * a.q_tiles * a.n_split;
-  attention_kernel<kEmu, kSplit><<<grid, att_threads<kSplit>(), ATT_SMEM_BYTES, stream>>>(tq, tkv, a);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(a.batch * a.heads * a.q_tiles * a.n_split);
+  cfg.blockDim = dim3(att_threads<kSplit>());
+  cfg.dynamicSmemBytes = ATT_SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  cfg.attrs = attr;
+  cfg.numAttrs = launch_attrs(attr, 1);
+  return cudaLaunchKernelEx(&cfg, attention_kernel<kEmu, kSplit>, tq, tkv, a);
 }
 
 #ifndef F3R_ATT_EMU_DEFAULT
@@ -443,6 +451,8 @@ cudaError_t launch_attention(const CUtensorMap& tq, const CUtensorMap& tkv, cons
 __global__ void __launch_bounds__(256) attention_merge_kernel(const float* __restrict__ part_o,
                                                               const float* __restrict__ part_lse, int n_parts, int batch,
                                                               int heads, int sq, __nv_bfloat16* __restrict__ out, int ldo) {
+  pdl_wait();                // the partials come from the preceding attention launches
+  pdl_launch_dependents();
   const size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   const size_t rows = static_cast<size_t>(batch) * sq;
   if (idx >= rows * heads * 8) return;
@@ -474,9 +484,15 @@ cudaError_t launch_attention_merge(const float* part_o, const float* part_lse, i
                                    void* out, int ldo, cudaStream_t stream) {
   const size_t total = static_cast<size_t>(batch) * sq * heads * 8;
   if (total == 0) return cudaSuccess;
-  attention_merge_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
-      part_o, part_lse, n_parts, batch, heads, sq, static_cast<__nv_bfloat16*>(out), ldo);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>((total + 255) / 256));
+  cfg.blockDim = dim3(256);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  cfg.attrs = attr;
+  cfg.numAttrs = launch_attrs(attr, 1);
+  return cudaLaunchKernelEx(&cfg, attention_merge_kernel, part_o, part_lse, n_parts, batch, heads, sq,
+                            static_cast<__nv_bfloat16*>(out), ldo);
 }
 
 }  // namespace f3r

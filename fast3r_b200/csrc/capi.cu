@@ -89,6 +89,11 @@ int f3r_set_option(const char* name, int32_t value) {
     f3r::g_attn_emu = value;
     return 0;
   }
+  if (!strcmp(name, "pdl")) {
+    if (value != 0 && value != 1) return fail("f3r_set_option: pdl must be 0 or 1");
+    f3r::g_pdl = value;
+    return 0;
+  }
   if (!strcmp(name, "attn_split")) {
     if (value != -1 && value != 1 && value != 2) return fail("f3r_set_option: attn_split must be -1, 1 or 2");
     f3r::g_attn_split = value;

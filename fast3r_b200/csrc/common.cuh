@@ -113,6 +113,15 @@ F3R_DEVICE void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" 
 F3R_DEVICE void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 F3R_DEVICE void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+// ------------------------------------------------------------------ programmatic dependent launch
+// Kernels of the hot chain are launched with cudaLaunchAttributeProgrammaticStreamSerialization (f3r::pdl_enabled()): the
+// next kernel's CTAs may become resident, run their prologue (barrier init, TMEM allocation, descriptor prefetch) and park
+// at pdl_wait() while the previous kernel drains its last wave.  pdl_wait() returns when ALL memory operations of the
+// preceding grid are complete and visible, so every access to global memory must come after it; pdl_launch_dependents()
+// only allows the successor to be scheduled early.  Without the launch attribute both are no-ops.
+F3R_DEVICE void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+F3R_DEVICE void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ------------------------------------------------------------------ thread-block clusters
 F3R_DEVICE uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 F3R_DEVICE uint32_t cluster_id_x() { uint32_t r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }

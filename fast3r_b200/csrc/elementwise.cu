@@ -1,9 +1,36 @@
 // HBM-bound helper kernels: LayerNorm (fp32 residual stream -> bf16 GEMM operand), patch im2col, strided
 // 3x3 im2col, bilinear x2 upsample (align_corners=True), fp32 -> bf16 cast.  All use 128-bit accesses.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "f3r_kernels.h"
 
 namespace f3r {
+
+int g_pdl = -1;
+bool pdl_enabled() {
+  if (g_pdl < 0) {
+    const char* e = getenv("F3R_PDL");
+    g_pdl = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_pdl == 1;
+}
+int launch_attrs(cudaLaunchAttribute* attr, int cluster) {
+  int n = 0;
+  if (cluster > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  return n;
+}
 
 // ---------------------------------------------------------------- LayerNorm
 // nn.LayerNorm over the last dim, biased variance, y = (x-mu)/sqrt(var+eps)*w+b.  One warp per row.
@@ -12,6 +39,8 @@ template <int VEC>  // dim = VEC * 128
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                         const float* __restrict__ b, void* __restrict__ out,
                                                         int out_f32, int rows, float eps) {
+  pdl_wait();                // x is written by the preceding GEMM
+  pdl_launch_dependents();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -58,14 +87,20 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 cudaError_t launch_layernorm(const float* x, const float* w, const float* b, void* out, int out_f32, int rows,
                              int dim, float eps, cudaStream_t stream) {
   if (rows <= 0) return cudaSuccess;
-  const int grid = (rows + 7) / 8;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((rows + 7) / 8);
+  cfg.blockDim = dim3(256);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  cfg.attrs = attr;
+  cfg.numAttrs = launch_attrs(attr, 1);
   switch (dim) {
-    case 128: layernorm_kernel<1><<<grid, 256, 0, stream>>>(x, w, b, out, out_f32, rows, eps); break;
-    case 256: layernorm_kernel<2><<<grid, 256, 0, stream>>>(x, w, b, out, out_f32, rows, eps); break;
-    case 384: layernorm_kernel<3><<<grid, 256, 0, stream>>>(x, w, b, out, out_f32, rows, eps); break;
-    case 512: layernorm_kernel<4><<<grid, 256, 0, stream>>>(x, w, b, out, out_f32, rows, eps); break;
-    case 768: layernorm_kernel<6><<<grid, 256, 0, stream>>>(x, w, b, out, out_f32, rows, eps); break;
-    case 1024: layernorm_kernel<8><<<grid, 256, 0, stream>>>(x, w, b, out, out_f32, rows, eps); break;
+    case 128: return cudaLaunchKernelEx(&cfg, layernorm_kernel<1>, x, w, b, out, out_f32, rows, eps);
+    case 256: return cudaLaunchKernelEx(&cfg, layernorm_kernel<2>, x, w, b, out, out_f32, rows, eps);
+    case 384: return cudaLaunchKernelEx(&cfg, layernorm_kernel<3>, x, w, b, out, out_f32, rows, eps);
+    case 512: return cudaLaunchKernelEx(&cfg, layernorm_kernel<4>, x, w, b, out, out_f32, rows, eps);
+    case 768: return cudaLaunchKernelEx(&cfg, layernorm_kernel<6>, x, w, b, out, out_f32, rows, eps);
+    case 1024: return cudaLaunchKernelEx(&cfg, layernorm_kernel<8>, x, w, b, out, out_f32, rows, eps);
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();

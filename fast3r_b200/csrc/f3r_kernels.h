@@ -6,6 +6,12 @@
 
 namespace f3r {
 
+// 1: launch the hot-chain kernels with programmatic stream serialization (PDL); F3R_PDL=0 / f3r_set_option("pdl", 0) disable
+extern int g_pdl;
+bool pdl_enabled();
+// fills `attr` (room for 2) with the cluster dimension (if cluster > 1) and the PDL attribute (if enabled); returns the count
+int launch_attrs(cudaLaunchAttribute* attr, int cluster);
+
 enum { EPI_STORE = 0, EPI_ROPE = 1, EPI_IDXEMB = 2, EPI_CONVT = 3, EPI_FINAL = 4 };
 enum { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2 };
 

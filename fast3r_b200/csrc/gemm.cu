@@ -316,6 +316,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   if constexpr (kCluster > 1) cluster_sync_all();  // peer barriers are initialised before any multicast can arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();                // operands / residual are produced by the preceding kernels: no global access above this line
+  pdl_launch_dependents();   // except the 1x1-conv weights of FINAL and the tensor-map prefetch (parameters, not activations)
 
   // work item = (group of kCluster vertically adjacent m-tiles, n-tile); both CTAs of a cluster walk the same items
   const int cta_rank = kCluster > 1 ? static_cast<int>(cluster_ctarank()) : 0;
@@ -497,13 +499,18 @@ static cudaError_t launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, c
   cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;  // (always set, also for kCluster == 1)
   attr[0].val.clusterDim.x = kCluster;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (pdl_enabled()) {
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 2;
+  }
   return cudaLaunchKernelEx(&cfg, gemm_kernel<BLOCK_N, kCluster>, ta, tb, to0, to0b, a);
 }
 

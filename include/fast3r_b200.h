@@ -78,7 +78,8 @@ uint64_t f3r_launch_count(void);
 
 /* Tuning knobs for A/B measurements (process-wide).  "attn_emu" = how many of every 8 exponential pairs of the
  * attention softmax are evaluated on the FMA pipe instead of MUFU.EX2 (0..3, -1 = built-in default); "attn_split" =
- * softmax threads per query row (1 or 2, -1 = default). */
+ * softmax threads per query row (1 or 2, -1 = default); "pdl" = 1 / 0: launch the GEMM / attention / LayerNorm chain with
+ * programmatic dependent launch (successor prologues overlap predecessor tails; default 1, env F3R_PDL=0 disables). */
 int f3r_set_option(const char* name, int32_t value);
 
 int f3r_gemm(const f3r_gemm_desc* d, void* stream);
