@@ -361,6 +361,58 @@ def ingest_rates(dev, hbm_gbs):
             "note": "decode (PIL, host threads) and the H2D copy of the decoded image are outside this number"}
 
 
+def geometry_rates(dev, hbm_gbs):
+    """SURVEY §8 f2 (first slice): align_local_pts3d_to_global for N=32 views at 512x368 - the GPU kernels (quantile, masked
+    moments + Umeyama, apply) on device-resident preds vs the oracle restatement on one host core for one view (the
+    reference runs one such task per (view, batch item) in a CPU thread pool), plus the 100-iteration Weiszfeld focal."""
+    import numpy as np
+    import torch
+    from fast3r_b200 import ops
+    from oracle import geometry_oracle as go
+    views, h, w = 32, 368, 512
+    n = h * w
+    g = torch.Generator(device=dev).manual_seed(0)
+    x = torch.randn(views, n, 3, device=dev, generator=g) + 2
+    y = 1.5 * x.flip(-1).contiguous() + 0.01 * torch.randn(views, n, 3, device=dev, generator=g)
+    conf = 1 + torch.exp(torch.randn(views, n, device=dev, generator=g))
+    out = torch.empty_like(x)
+
+    def align():
+        thr = ops.conf_quantile(conf, 0.3)
+        ops.similarity_apply(x, ops.similarity_fit(x, y, conf, thr), out)
+
+    def timed(fn, reps):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps * 1e3
+
+    us = timed(align, 20)
+    nbytes = views * n * (5 * 4 + 28 + 24)  # 5 quantile passes over conf; fit reads x, y, conf; apply reads x, writes out
+    pts = x.reshape(views, h, w, 3)
+    cmap = conf.reshape(views, h, w)
+    thr10 = ops.conf_quantile(conf, 0.1)
+    us_f = timed(lambda: ops.focal_weiszfeld(pts[:1], cmap[:1], thr10[:1], None, iters=100), 5)
+    t0 = time.time()
+    go.align_local_to_global(x[0].reshape(h, w, 3).cpu().numpy(), cmap[0].cpu().numpy(), y[0].reshape(h, w, 3).cpu().numpy(), None, 30.0)
+    cpu_ms = (time.time() - t0) * 1e3
+    t0 = time.time()
+    go.estimate_focal(pts[0].cpu().numpy(), cmap[0].cpu().numpy())
+    cpu_f_ms = (time.time() - t0) * 1e3
+    return {"workload": "align_local_pts3d_to_global, 32 views 512x368, 30th-percentile confidence mask",
+            "gpu_us_per_32_views": us, "gpu_views_per_sec": views / us * 1e6, "algorithmic_bytes": nbytes,
+            "achieved_gbs": nbytes / us / 1e3, "frac_of_measured_hbm": nbytes / us / 1e3 / hbm_gbs,
+            "oracle_cpu_ms_per_view_1_core": cpu_ms, "focal_weiszfeld_100it_gpu_us_per_view": us_f,
+            "focal_oracle_cpu_ms_per_view_1_core": cpu_f_ms,
+            "note": "inputs resident in HBM; PnP-RANSAC (fast_pnp) is not part of this slice"}
+
+
 def attention_roofline(timer, n_views, ms_step, clocks, peak_tf, peak_src):
     att = [(b, h, sq, skv, a.elapsed_time(z)) for (b, h, sq, skv, a, z) in timer if skv == n_views * P_TOK]
     if not att:
@@ -561,6 +613,10 @@ def run_ours(args, rank, world, local_rank):
                 extra["ingest_12mpix"] = ingest_rates(dev, hbm)
             except Exception as e:  # context only
                 extra["ingest_12mpix"] = {"unavailable": repr(e)[:200]}
+            try:
+                extra["geometry_tail_N32"] = geometry_rates(dev, hbm)
+            except Exception as e:  # context only
+                extra["geometry_tail_N32"] = {"unavailable": repr(e)[:200]}
     if rank == 0 and world == 1 and not args.no_extras and not args.no_library_bar:
         extra["library_bar_N32"] = library_bar(32, dev)
     if rank != 0:

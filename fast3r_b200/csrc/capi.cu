@@ -416,6 +416,52 @@ int f3r_ingest_rgb8(const uint8_t* src, int32_t h, int32_t w, int32_t oh, int32_
                                   static_cast<cudaStream_t>(stream)), "f3r_ingest_rgb8");
 }
 
+// ---------------------------------------------------------------- geometry tail
+int f3r_conf_quantile(const float* conf, int32_t views, int32_t n, float q, float* thr, void* stream) {
+  if (!conf || !thr) return fail("f3r_conf_quantile: null operand");
+  if (views <= 0 || n <= 0 || n > (1 << 24)) return fail("f3r_conf_quantile: bad shape (n must be in [1, 2^24]: ranks are fp32)");
+  if (!(q >= 0.f && q <= 1.f)) return fail("f3r_conf_quantile: q must be in [0, 1]");
+  g_launches++;
+  return check(f3r::launch_conf_quantile(conf, views, n, q, thr, static_cast<cudaStream_t>(stream)), "f3r_conf_quantile");
+}
+
+size_t f3r_similarity_fit_workspace(int32_t views) { return views > 0 ? f3r::similarity_fit_workspace(views) : 0; }
+
+int f3r_similarity_fit(const float* x, const float* y, const float* conf, const float* thr, const uint8_t* valid,
+                       int32_t views, int32_t n, float* rts, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!x || !y || !rts || !workspace) return fail("f3r_similarity_fit: null operand");
+  if (views <= 0 || views > 65535 || n <= 0 || n > (1 << 29)) return fail("f3r_similarity_fit: bad shape");
+  if ((conf != nullptr) != (thr != nullptr)) return fail("f3r_similarity_fit: conf and thr must be given together");
+  if (workspace_bytes < f3r::similarity_fit_workspace(views)) return fail("f3r_similarity_fit: workspace too small");
+  if (reinterpret_cast<uintptr_t>(workspace) & 7) return fail("f3r_similarity_fit: workspace not 8-byte aligned");
+  g_launches += 2;
+  return check(f3r::launch_similarity_fit(x, y, conf, thr, valid, views, n, rts, static_cast<double*>(workspace),
+                                          static_cast<cudaStream_t>(stream)), "f3r_similarity_fit");
+}
+
+int f3r_similarity_apply(const float* x, const float* rts, float* out, int32_t views, int32_t n, void* stream) {
+  if (!x || !rts || !out) return fail("f3r_similarity_apply: null operand");
+  if (views <= 0 || views > 65535 || n <= 0 || n > (1 << 29)) return fail("f3r_similarity_apply: bad shape");
+  g_launches++;
+  return check(f3r::launch_similarity_apply(x, rts, out, views, n, static_cast<cudaStream_t>(stream)), "f3r_similarity_apply");
+}
+
+size_t f3r_focal_workspace(int32_t views) { return views > 0 ? f3r::focal_workspace(views) : 0; }
+
+int f3r_focal_weiszfeld(const float* pts, const float* conf, const float* thr, const float* pp, int32_t views, int32_t h,
+                        int32_t w, int32_t iters, float* focal, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!pts || !focal || !workspace) return fail("f3r_focal_weiszfeld: null operand");
+  if (views <= 0 || views > 65535 || h <= 0 || w <= 0 || static_cast<int64_t>(h) * w > (1 << 29))
+    return fail("f3r_focal_weiszfeld: bad shape");
+  if (iters < 0 || iters > 10000) return fail("f3r_focal_weiszfeld: bad iteration count");
+  if ((conf != nullptr) != (thr != nullptr)) return fail("f3r_focal_weiszfeld: conf and thr must be given together");
+  if (workspace_bytes < f3r::focal_workspace(views)) return fail("f3r_focal_weiszfeld: workspace too small");
+  if (reinterpret_cast<uintptr_t>(workspace) & 7) return fail("f3r_focal_weiszfeld: workspace not 8-byte aligned");
+  g_launches += static_cast<uint64_t>(iters) + 2;
+  return check(f3r::launch_focal_weiszfeld(pts, conf, thr, pp, views, h, w, iters, focal, static_cast<double*>(workspace),
+                                           static_cast<cudaStream_t>(stream)), "f3r_focal_weiszfeld");
+}
+
 // ---------------------------------------------------------------- block-level entry points
 size_t f3r_transformer_workspace(int32_t rows, int32_t dim, int32_t hidden) {
   // h [rows, dim] | q [rows, dim] | kv [rows, 2 dim] | att [rows, dim] | hid [rows, hidden], bf16, 256-byte aligned parts

@@ -95,4 +95,15 @@ cudaError_t launch_ingest(const uint8_t* src, int h, int w, int oh, int ow, cons
                           int h_span_max, const int32_t* vb, const int32_t* vk, int vks, uint8_t* tmp, int left, int top,
                           int cw, int ch, float* out, cudaStream_t stream);
 
+// geometry tail (geometry.cu)
+cudaError_t launch_conf_quantile(const float* conf, int views, int n, float q, float* thr, cudaStream_t stream);
+size_t similarity_fit_workspace(int views);
+cudaError_t launch_similarity_fit(const float* x, const float* y, const float* conf, const float* thr,
+                                  const uint8_t* valid, int views, int n, float* rts, double* workspace,
+                                  cudaStream_t stream);
+cudaError_t launch_similarity_apply(const float* x, const float* rts, float* out, int views, int n, cudaStream_t stream);
+size_t focal_workspace(int views);
+cudaError_t launch_focal_weiszfeld(const float* pts, const float* conf, const float* thr, const float* pp, int views,
+                                   int H, int W, int iters, float* focal, double* workspace, cudaStream_t stream);
+
 }  // namespace f3r

@@ -46,7 +46,8 @@ EXPORTS = ["f3r_last_error", "f3r_abi_version", "f3r_gemm_desc_size", "f3r_launc
            "f3r_layernorm", "f3r_im2col_patch", "f3r_im2col3x3s2", "f3r_upsample2x", "f3r_cast_bf16", "f3r_split3",
            "f3r_add_f32", "f3r_attention_x3_workspace", "f3r_attention_x3", "f3r_set_option", "f3r_attention_partial",
            "f3r_attention_merge", "f3r_resample_ksize", "f3r_resample_coeffs", "f3r_ingest_rgb8",
-           "f3r_transformer_workspace", "f3r_transformer_blocks"]
+           "f3r_transformer_workspace", "f3r_transformer_blocks", "f3r_conf_quantile", "f3r_similarity_fit_workspace",
+           "f3r_similarity_fit", "f3r_similarity_apply", "f3r_focal_workspace", "f3r_focal_weiszfeld"]
 
 _lib = None
 
@@ -86,6 +87,18 @@ def load() -> C.CDLL:
                                            C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_int32, C.c_int32, C.c_void_p,
                                            C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     lib.f3r_transformer_blocks.restype = C.c_int
+    lib.f3r_conf_quantile.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_void_p]
+    lib.f3r_similarity_fit_workspace.argtypes = [C.c_int32]
+    lib.f3r_similarity_fit_workspace.restype = C.c_size_t
+    lib.f3r_similarity_fit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                       C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.f3r_similarity_apply.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+    lib.f3r_focal_workspace.argtypes = [C.c_int32]
+    lib.f3r_focal_workspace.restype = C.c_size_t
+    lib.f3r_focal_weiszfeld.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                        C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    for name in ("f3r_conf_quantile", "f3r_similarity_fit", "f3r_similarity_apply", "f3r_focal_weiszfeld"):
+        getattr(lib, name).restype = C.c_int
     lib.f3r_set_option.argtypes = [C.c_char_p, C.c_int32]
     lib.f3r_set_option.restype = C.c_int
     lib.f3r_attention.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,

@@ -289,3 +289,75 @@ def cast_bf16(x: torch.Tensor, out: torch.Tensor):
     assert x.numel() == out.numel()
     with _on_device(x):
         L.check(L.load().f3r_cast_bf16(_ptr(x), _ptr(out), x.numel(), _stream(x)), "f3r_cast_bf16")
+
+
+# ------------------------------------------------------------------ geometry tail (csrc/geometry.cu)
+def conf_quantile(conf: torch.Tensor, q: float) -> torch.Tensor:
+    """conf fp32 [views, n] -> thr fp32 [views] = torch.quantile(conf[v], q) (exact, linear interpolation)."""
+    _chk(conf, F32, "conf")
+    assert conf.dim() == 2
+    thr = torch.empty(conf.shape[0], dtype=F32, device=conf.device)
+    with _on_device(conf):
+        L.check(L.load().f3r_conf_quantile(_ptr(conf), conf.shape[0], conf.shape[1], float(q), _ptr(thr), _stream(conf)),
+                "f3r_conf_quantile")
+    return thr
+
+
+def similarity_fit(x: torch.Tensor, y: torch.Tensor, conf: Optional[torch.Tensor] = None,
+                   thr: Optional[torch.Tensor] = None, valid: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x, y fp32 [views, n, 3]; conf fp32 [views, n] with thr fp32 [views]; valid uint8 [views, n].  Returns rts
+    fp32 [views, 13] (R row-major, t, s) with y ~ s R x + t over conf >= thr & valid (fallbacks as the reference)."""
+    _chk(x, F32, "x"); _chk(y, F32, "y")
+    views, n = x.shape[0], x.shape[1]
+    assert x.shape == y.shape == (views, n, 3)
+    if conf is not None:
+        _chk(conf, F32, "conf"); _chk(thr, F32, "thr")
+        assert conf.shape == (views, n) and thr.shape == (views,)
+    if valid is not None:
+        _chk(valid, torch.uint8, "valid")
+        assert valid.shape == (views, n)
+    lib = L.load()
+    nbytes = lib.f3r_similarity_fit_workspace(views)
+    ws = torch.empty(nbytes // 8, dtype=torch.float64, device=x.device)
+    rts = torch.empty(views, 13, dtype=F32, device=x.device)
+    with _on_device(x):
+        L.check(lib.f3r_similarity_fit(_ptr(x), _ptr(y), _ptr(conf), _ptr(thr), _ptr(valid), views, n, _ptr(rts), _ptr(ws),
+                                       nbytes, _stream(x)), "f3r_similarity_fit")
+    return rts
+
+
+def similarity_apply(x: torch.Tensor, rts: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[v] = s_v (x[v] R_v^T) + t_v, fp32 [views, n, 3]."""
+    _chk(x, F32, "x"); _chk(rts, F32, "rts")
+    views, n = x.shape[0], x.shape[1]
+    assert x.shape == (views, n, 3) and rts.shape == (views, 13)
+    if out is None:
+        out = torch.empty_like(x)
+    _chk(out, F32, "out")
+    assert out.shape == x.shape
+    with _on_device(x):
+        L.check(L.load().f3r_similarity_apply(_ptr(x), _ptr(rts), _ptr(out), views, n, _stream(x)), "f3r_similarity_apply")
+    return out
+
+
+def focal_weiszfeld(pts: torch.Tensor, conf: Optional[torch.Tensor] = None, thr: Optional[torch.Tensor] = None,
+                    pp: Optional[torch.Tensor] = None, iters: int = 100) -> torch.Tensor:
+    """pts fp32 [views, H, W, 3]; conf fp32 [views, H, W] with thr fp32 [views]; pp fp32 [views, 2] or None (image
+    centre).  Returns focal fp32 [views]."""
+    _chk(pts, F32, "pts")
+    views, h, w = pts.shape[0], pts.shape[1], pts.shape[2]
+    assert pts.shape == (views, h, w, 3)
+    if conf is not None:
+        _chk(conf, F32, "conf"); _chk(thr, F32, "thr")
+        assert conf.shape == (views, h, w) and thr.shape == (views,)
+    if pp is not None:
+        _chk(pp, F32, "pp")
+        assert pp.shape == (views, 2)
+    lib = L.load()
+    nbytes = lib.f3r_focal_workspace(views)
+    ws = torch.empty(nbytes // 8, dtype=torch.float64, device=pts.device)
+    focal = torch.empty(views, dtype=F32, device=pts.device)
+    with _on_device(pts):
+        L.check(lib.f3r_focal_weiszfeld(_ptr(pts), _ptr(conf), _ptr(thr), _ptr(pp), views, h, w, int(iters), _ptr(focal),
+                                        _ptr(ws), nbytes, _stream(pts)), "f3r_focal_weiszfeld")
+    return focal

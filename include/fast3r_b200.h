@@ -151,6 +151,31 @@ int f3r_ingest_rgb8(const uint8_t* src, int32_t h, int32_t w, int32_t oh, int32_
                     int32_t hks, int32_t h_span_max, const int32_t* vb, const int32_t* vk, int32_t vks, uint8_t* tmp,
                     int32_t left, int32_t top, int32_t cw, int32_t ch, float* out, void* stream);
 
+/* ---- geometry tail (first slice): what every caller runs on the forward's outputs before poses.
+ * A "view" below is one (view, batch item) pointmap of n = H*W pixels; all arrays are DEVICE pointers, fp32, view-major.
+ *
+ * f3r_conf_quantile: thr[v] = torch.quantile(conf[v].reshape(-1), q) (linear interpolation, fp32 like ATen) - the
+ *   confidence threshold of align_local_pts3d_to_global (fast3r/models/multiview_dust3r_module.py:477) and of
+ *   estimate_focal (:1093).  Exact: radix select on the float bit patterns.
+ * f3r_similarity_fit: per view the least-squares similarity (R, t, s), y ~ s R x + t, over the pixels with
+ *   conf >= thr & valid; fewer than 3 such pixels -> over valid only; still fewer -> identity (:480-515, where the fit is
+ *   roma.rigid_points_registration(x, y, compute_scaling=True)).  conf/thr and valid may be NULL (no such mask).
+ *   rts [views][13] = R row-major (9), t (3), s.  workspace: f3r_similarity_fit_workspace(views) bytes, 8-byte aligned.
+ * f3r_similarity_apply: out = s (x R^T) + t on all n pixels of every view (:517-521).  out may alias x.
+ * f3r_focal_weiszfeld: focal[v] = argmin_f sum |pixel - pp - f (x, y)/z| by `iters` IRLS steps from the L2 closed form,
+ *   over the pixels with conf >= thr (conf/thr NULL: all pixels), clipped to [0, inf); no selected pixel -> max(H, W) /
+ *   (2 tan 30 deg).  iters = 100 with a mask reproduces estimate_focal_knowing_depth_and_confidence_mask(weiszfeld)
+ *   (fast3r/dust3r/post_process.py:82-142), iters = 10 without one estimate_focal_knowing_depth(weiszfeld) (:19-79).
+ *   pts [views][H][W][3]; pp [views][2] or NULL (= (W/2, H/2)).  workspace: f3r_focal_workspace(views) bytes. */
+int f3r_conf_quantile(const float* conf, int32_t views, int32_t n, float q, float* thr, void* stream);
+size_t f3r_similarity_fit_workspace(int32_t views);
+int f3r_similarity_fit(const float* x, const float* y, const float* conf, const float* thr, const uint8_t* valid,
+                       int32_t views, int32_t n, float* rts, void* workspace, size_t workspace_bytes, void* stream);
+int f3r_similarity_apply(const float* x, const float* rts, float* out, int32_t views, int32_t n, void* stream);
+size_t f3r_focal_workspace(int32_t views);
+int f3r_focal_weiszfeld(const float* pts, const float* conf, const float* thr, const float* pp, int32_t views, int32_t h,
+                        int32_t w, int32_t iters, float* focal, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- parity mode: the reference's fp32 path (inference_multiview.py:41-49, dtype="32": no autocast) on the bf16
  * tensor pipe.  Every fp32 operand x is carried as hi + lo (two bf16), every product as hi*hi + lo*hi + hi*lo with
  * fp32 accumulation.  For f3r_gemm this is the ordinary kernel over a 3x longer K: A' = f3r_split3(A) = [hi|lo|hi],

@@ -64,3 +64,58 @@ def import_reference():
     from fast3r.dust3r.inference_multiview import inference
 
     return Fast3R, inference
+
+
+def import_reference_lit_module(roma_registration=None):
+    """The reference's Lightning module (fast3r/models/multiview_dust3r_module.py) with in-memory stand-ins for the
+    training-stack packages this image lacks (module lines 1-29: roma, lightning, torchmetrics, pl_bolts, open3d).
+    `roma_registration(x, y, compute_scaling=True) -> (R, t, s)` becomes ``roma.rigid_points_registration`` - roma is
+    not installable here, see oracle/geometry_oracle.py."""
+    import torch
+    import torch.nn as nn
+
+    import_reference()
+
+    def mod(name, **attrs):
+        m = sys.modules.get(name) or types.ModuleType(name)
+        for k, v in attrs.items():
+            setattr(m, k, v)
+        sys.modules[name] = m
+        return m
+
+    class LightningModule(nn.Module):
+        def save_hyperparameters(self, *a, **k):
+            pass
+
+        @property
+        def device(self):
+            return torch.device("cpu")
+
+    class _Metric(nn.Module):
+        def __init__(self, *a, **k):
+            super().__init__()
+
+        def update(self, *a, **k):
+            pass
+
+        def compute(self):
+            return torch.tensor(0.0)
+
+    class BaseAggregator(_Metric):
+        def __init__(self, fn=None, default_value=None, nan_strategy=None, state_name="value", **k):
+            super().__init__()
+            setattr(self, state_name, default_value)
+
+    for name in ("open3d", "pl_bolts", "pl_bolts.optimizers", "lightning.pytorch", "lightning.pytorch.loggers"):
+        mod(name)
+    roma = mod("roma")
+    if roma_registration is not None:
+        roma.rigid_points_registration = roma_registration
+    mod("lightning", LightningModule=LightningModule)
+    mod("lightning.pytorch.loggers.wandb", WandbLogger=type("WandbLogger", (), {}))
+    mod("torchmetrics", MaxMetric=_Metric, MeanMetric=_Metric, MinMetric=_Metric, SumMetric=_Metric, Metric=_Metric)
+    mod("torchmetrics.aggregation", BaseAggregator=BaseAggregator)
+    mod("pl_bolts.optimizers.lr_scheduler", LinearWarmupCosineAnnealingLR=type("LinearWarmupCosineAnnealingLR", (), {}))
+    import fast3r.models.multiview_dust3r_module as lit_mod
+
+    return lit_mod

@@ -207,3 +207,70 @@ def upsample2x(x, out, n, h, w, c, ho, wo):
 
 def cast_bf16(x, out):
     _store(out, x)
+
+
+# ------------------------------------------------------------------ geometry tail (csrc/geometry.cu)
+def conf_quantile(conf, q):
+    return torch.stack([torch.quantile(c, float(q)) for c in conf])
+
+
+def similarity_fit(x, y, conf=None, thr=None, valid=None):
+    """Same reduction the kernel does: 17 raw moments per point set in fp64, then Umeyama from the moments."""
+    views, n, _ = x.shape
+    rts = torch.zeros(views, 13, dtype=F32)
+    for v in range(views):
+        vm = torch.ones(n, dtype=torch.bool) if valid is None else valid[v].bool()
+        sel = vm if conf is None else (vm & (conf[v] >= thr[v]))
+        if sel.sum() < 3:
+            sel = vm
+        if sel.sum() < 3:
+            rts[v, 0] = rts[v, 4] = rts[v, 8] = rts[v, 12] = 1.0
+            continue
+        a, b = x[v][sel].double(), y[v][sel].double()
+        cnt = a.shape[0]
+        xm, ym = a.sum(0) / cnt, b.sum(0) / cnt
+        m = b.T @ a - cnt * torch.outer(ym, xm)
+        var = (a * a).sum() - cnt * (xm * xm).sum()
+        u, s, vt = torch.linalg.svd(m)
+        d = torch.sign(torch.det(u @ vt))
+        dd = torch.tensor([1.0, 1.0, float(d) if d != 0 else 1.0], dtype=torch.float64)
+        r = (u * dd) @ vt
+        sc = (s * dd).sum() / var
+        rts[v, :9] = r.reshape(-1).float()
+        rts[v, 9:12] = (ym - sc * (r @ xm)).float()
+        rts[v, 12] = sc.float()
+    return rts
+
+
+def similarity_apply(x, rts, out=None):
+    r = rts[:, :9].reshape(-1, 3, 3)
+    res = rts[:, 12].reshape(-1, 1, 1) * (x @ r.transpose(1, 2)) + rts[:, 9:12].reshape(-1, 1, 3)
+    if out is None:
+        return res
+    out.copy_(res)
+    return out
+
+
+def focal_weiszfeld(pts, conf=None, thr=None, pp=None, iters=100):
+    views, h, w, _ = pts.shape
+    out = torch.zeros(views, dtype=F32)
+    vv, uu = torch.meshgrid(torch.arange(h, dtype=F32), torch.arange(w, dtype=F32), indexing="ij")
+    for v in range(views):
+        cx, cy = (w / 2, h / 2) if pp is None else (float(pp[v, 0]), float(pp[v, 1]))
+        px = torch.stack([uu - cx, vv - cy], -1).reshape(-1, 2)
+        p = pts[v].reshape(-1, 3)
+        if conf is not None:
+            sel = (conf[v] >= thr[v]).reshape(-1)
+            p, px = p[sel], px[sel]
+        if p.shape[0] == 0:
+            out[v] = max(h, w) / (2 * math.tan(math.radians(30)))
+            continue
+        xyz = (p[:, :2] / p[:, 2:3]).nan_to_num(nan=0.0, posinf=0.0, neginf=0.0)
+        dpx, dxx = (xyz * px).sum(-1).double(), (xyz * xyz).sum(-1).double()
+        f = dpx.sum() / dxx.sum()
+        for _ in range(iters):
+            dis = (px - f.float() * xyz).norm(dim=-1)
+            wgt = dis.clip(min=1e-8).reciprocal().double()
+            f = (wgt * dpx).sum() / (wgt * dxx).sum()
+        out[v] = max(float(f), 0.0)
+    return out
