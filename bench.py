@@ -394,6 +394,11 @@ def geometry_rates(dev, hbm_gbs):
         return e0.elapsed_time(e1) / reps * 1e3
 
     us = timed(align, 20)
+    thr30 = ops.conf_quantile(conf, 0.3)
+    rts30 = ops.similarity_fit(x, y, conf, thr30)
+    parts = {"quantile": timed(lambda: ops.conf_quantile(conf, 0.3), 20),
+             "fit": timed(lambda: ops.similarity_fit(x, y, conf, thr30), 20),
+             "apply": timed(lambda: ops.similarity_apply(x, rts30, out), 20)}
     nbytes = views * n * (5 * 4 + 28 + 24)  # 5 quantile passes over conf; fit reads x, y, conf; apply reads x, writes out
     pts = x.reshape(views, h, w, 3)
     cmap = conf.reshape(views, h, w)
@@ -408,6 +413,7 @@ def geometry_rates(dev, hbm_gbs):
     return {"workload": "align_local_pts3d_to_global, 32 views 512x368, 30th-percentile confidence mask",
             "gpu_us_per_32_views": us, "gpu_views_per_sec": views / us * 1e6, "algorithmic_bytes": nbytes,
             "achieved_gbs": nbytes / us / 1e3, "frac_of_measured_hbm": nbytes / us / 1e3 / hbm_gbs,
+            "gpu_us_by_kernel": parts, "apply_gbs": views * n * 24 / parts["apply"] / 1e3,
             "oracle_cpu_ms_per_view_1_core": cpu_ms, "focal_weiszfeld_100it_gpu_us_per_view": us_f,
             "focal_oracle_cpu_ms_per_view_1_core": cpu_f_ms,
             "note": "inputs resident in HBM; PnP-RANSAC (fast_pnp) is not part of this slice"}

@@ -78,8 +78,11 @@ __global__ void __launch_bounds__(QT) conf_quantile_kernel(const float* __restri
     mask |= 0xffu << shift;
   }
   const uint32_t u_lo = prefix;
-  if (hi == lo) {
-    if (tid == 0) thr[blockIdx.x] = fkey_inv(u_lo);
+  if (hi == lo) {  // integral rank: ATen still evaluates lerp(a, a, 0) = fma(0, a - a, a), which is NaN for an infinite a
+    if (tid == 0) {
+      const float a = fkey_inv(u_lo);
+      thr[blockIdx.x] = fmaf(w, __fsub_rn(a, a), a);
+    }
     return;
   }
   if (tid == 0) {

@@ -37,9 +37,12 @@ def test_quantile_is_exact(ops):
         for q in (0.0, 0.1, 0.3, 0.5, 0.85, 0.999, 1.0):
             got = ops.conf_quantile(conf.cuda(), q).cpu()
             want = torch.stack([torch.quantile(c, q) for c in conf])
-            assert torch.equal(got, want), (views, n, q, got, want)
-            for v in range(views):
-                assert float(got[v]) == float(go.conf_quantile(conf[v].numpy(), q))
+            same = (got == want) | (got.isnan() & want.isnan())  # an infinite order statistic interpolates to NaN in ATen
+            assert bool(same.all()), (views, n, q, got, want)
+            with np.errstate(invalid="ignore"):
+                for v in range(views):
+                    o = float(go.conf_quantile(conf[v].numpy(), q))
+                    assert float(got[v]) == o or (np.isnan(o) and bool(got[v].isnan()))
 
 
 def test_quantile_mask_matches_torch_at_full_size(ops):
