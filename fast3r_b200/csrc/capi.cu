@@ -434,7 +434,7 @@ int f3r_similarity_fit(const float* x, const float* y, const float* conf, const 
   if ((conf != nullptr) != (thr != nullptr)) return fail("f3r_similarity_fit: conf and thr must be given together");
   if (workspace_bytes < f3r::similarity_fit_workspace(views)) return fail("f3r_similarity_fit: workspace too small");
   if (reinterpret_cast<uintptr_t>(workspace) & 7) return fail("f3r_similarity_fit: workspace not 8-byte aligned");
-  g_launches += 2;
+  g_launches += conf ? 4 : 2;
   return check(f3r::launch_similarity_fit(x, y, conf, thr, valid, views, n, rts, static_cast<double*>(workspace),
                                           static_cast<cudaStream_t>(stream)), "f3r_similarity_fit");
 }

@@ -318,7 +318,7 @@ def similarity_fit(x: torch.Tensor, y: torch.Tensor, conf: Optional[torch.Tensor
         assert valid.shape == (views, n)
     lib = L.load()
     nbytes = lib.f3r_similarity_fit_workspace(views)
-    ws = torch.empty(nbytes // 8, dtype=torch.float64, device=x.device)
+    ws = torch.empty((nbytes + 7) // 8, dtype=torch.float64, device=x.device)
     rts = torch.empty(views, 13, dtype=F32, device=x.device)
     with _on_device(x):
         L.check(lib.f3r_similarity_fit(_ptr(x), _ptr(y), _ptr(conf), _ptr(thr), _ptr(valid), views, n, _ptr(rts), _ptr(ws),
@@ -355,7 +355,7 @@ def focal_weiszfeld(pts: torch.Tensor, conf: Optional[torch.Tensor] = None, thr:
         assert pp.shape == (views, 2)
     lib = L.load()
     nbytes = lib.f3r_focal_workspace(views)
-    ws = torch.empty(nbytes // 8, dtype=torch.float64, device=pts.device)
+    ws = torch.empty((nbytes + 7) // 8, dtype=torch.float64, device=pts.device)
     focal = torch.empty(views, dtype=F32, device=pts.device)
     with _on_device(pts):
         L.check(lib.f3r_focal_weiszfeld(_ptr(pts), _ptr(conf), _ptr(thr), _ptr(pp), views, h, w, int(iters), _ptr(focal),
