@@ -79,7 +79,7 @@ def _align_group(group: List[Dict], gviews: List[Dict], q: float, dev: torch.dev
     for i, p in enumerate(group):
         src = p["pts3d_local"]
         aligned = out[i * b:(i + 1) * b].reshape(b, h, w, 3)
-        p["pts3d_local_aligned_to_global"] = aligned.to(device=src.device, dtype=src.dtype) if not src.is_cuda or src.dtype != torch.float32 else aligned
+        p["pts3d_local_aligned_to_global"] = aligned.to(device=src.device, dtype=src.dtype)  # no copy if already there
 
 
 def estimate_focal(pts3d_i: torch.Tensor, conf_i: torch.Tensor, pp: Optional[torch.Tensor] = None,
