@@ -178,3 +178,36 @@ def test_pick_kv_split_invariants():
     assert pick_kv_split(368, 184) == 2      # 4 GPUs
     assert pick_kv_split(1472, 184) == 1     # one GPU
     assert pick_kv_split(192, 23) == 1       # N=4: slices would be too short
+
+
+def test_cabi_rejects_bad_arguments_before_any_cuda_call():
+    """Argument validation of the C ABI runs before the first CUDA call, so it is checkable without a GPU: every entry
+    point returns non-zero and leaves a message naming itself in f3r_last_error()."""
+    import ctypes as C
+    from fast3r_b200 import lib as L
+    lib = L.load()
+    f = C.c_float
+    cases = [
+        ("f3r_conf_quantile", (None, 1, 10, f(0.5), None, None), "null operand"),
+        ("f3r_conf_quantile", (8, 1, 10, f(1.5), 8, None), "q must be in [0, 1]"),
+        ("f3r_conf_quantile", (8, 1, 1 << 25, f(0.5), 8, None), "bad shape"),
+        ("f3r_similarity_fit", (8, 8, 8, None, None, 1, 10, 8, 8, 10 ** 6, None), "conf and thr must be given together"),
+        ("f3r_similarity_fit", (8, 8, None, None, None, 1, 10, 8, 8, 16, None), "workspace too small"),
+        ("f3r_similarity_fit", (8, 8, None, None, None, 1, 10, 8, 9, 10 ** 6, None), "not 8-byte aligned"),
+        ("f3r_similarity_fit", (8, 8, None, None, None, 70000, 10, 8, 8, 10 ** 9, None), "bad shape"),
+        ("f3r_similarity_apply", (8, None, 8, 1, 10, None), "null operand"),
+        ("f3r_focal_weiszfeld", (8, None, None, None, 1, 4, 4, -1, 8, 8, 10 ** 6, None), "bad iteration count"),
+        ("f3r_focal_weiszfeld", (8, 8, None, None, 1, 4, 4, 10, 8, 8, 10 ** 6, None), "conf and thr must be given together"),
+        ("f3r_focal_weiszfeld", (8, None, None, None, 1, 4, 4, 10, 8, 8, 16, None), "workspace too small"),
+        ("f3r_layernorm", (None, None, None, None, 0, 1, 1024, f(1e-6), None), "null operand"),
+        ("f3r_attention", (None, 0, None, 0, None, 0, None, 1, 16, 128, 128, f(0.125), None), "null operand"),
+    ]
+    for name, args, msg in cases:
+        assert getattr(lib, name)(*args) != 0, name
+        err = lib.f3r_last_error().decode()
+        assert err.startswith(name) and msg in err, (name, err)
+    # workspace queries are pure host functions
+    assert lib.f3r_similarity_fit_workspace(0) == 0 and lib.f3r_similarity_fit_workspace(3) % 8 == 0
+    assert lib.f3r_focal_workspace(2) == 2 * 2 * 256 * 3 * 8
+    with pytest.raises(RuntimeError, match="f3r_conf_quantile failed"):
+        L.check(lib.f3r_conf_quantile(None, 1, 10, f(0.5), None, None), "f3r_conf_quantile")
