@@ -93,3 +93,25 @@ def test_reflection_planar_and_collinear_inputs(hostlib):
     r, t, s = solve(hostlib, xl, yl)
     assert np.isfinite(r).all() and abs(np.linalg.det(r) - 1) < 1e-5 and abs(s - 1.5) < 1e-5
     assert np.allclose(s * xl @ r.T + t, yl, atol=1e-5)
+
+
+def test_scale_extremes_and_near_isotropic_clouds(hostlib):
+    """Pointmaps in millimetres or kilometres, and clouds whose covariance is nearly a multiple of the identity (all three
+    singular values of M close together - the eigenvectors are then arbitrary, the rotation is not)."""
+    rng = np.random.default_rng(4)
+    for unit in (1e-4, 1.0, 1e4):
+        for _ in range(20):
+            x = rng.standard_normal((2000, 3)) * unit + rng.standard_normal(3) * 10 * unit
+            q = rot(rng)
+            s_true = rng.uniform(0.3, 3)
+            y = s_true * x @ q.T + rng.standard_normal(3) * unit + 1e-3 * unit * rng.standard_normal(x.shape)
+            r, t, s = solve(hostlib, x, y)
+            r0, t0, s0 = go.umeyama(x, y)
+            assert np.allclose(r, r0, atol=2e-6), unit
+            assert abs(s - s0) <= 2e-6 * s0, unit
+            assert np.allclose(t, t0, atol=3e-5 * unit * 30), unit
+    # exactly isotropic second moments: the 8 corners of a cube
+    cube = np.array([[i, j, k] for i in (-1.0, 1.0) for j in (-1.0, 1.0) for k in (-1.0, 1.0)])
+    q = rot(rng)
+    r, t, s = solve(hostlib, cube, 2.5 * cube @ q.T + np.array([1.0, 2.0, 3.0]))
+    assert np.allclose(r, q, atol=1e-6) and abs(s - 2.5) < 1e-6 and np.allclose(t, [1, 2, 3], atol=1e-5)
